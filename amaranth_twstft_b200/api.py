@@ -1,0 +1,169 @@
+"""Host-side mirror of the reference's per-second correlator interface over the C ABI.
+
+Reference seams mirrored here (paths relative to the reference root):
+  Correlator.process          record loop of processing/Octave/godual_ranging.m:75-102
+  Correlator.process_windows  processing(d,k,df) of acquisition/claudio_aligned_code_lo_separate.m:24-77
+  Correlator.estimate_carrier godual_ranging.m:14-15
+  Correlator.gen_code/set_code  amaranth_twstft/common.py:59-73 / godual_ranging.m:62-66
+Results come back as a numpy structured array whose field names are the reference's .mat
+variable names (indice, correction, SNRr, SNRi, df, puissance, puissancecode, puissancenoise, xval*).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+RESULT_DTYPE = np.dtype([(n, np.float64) for n in _lib.RESULT_FIELDS])
+
+
+class TwstftError(RuntimeError):
+    pass
+
+
+class Correlator:
+    """One plan = one GPU.  Not re-entrant; use one Correlator per host thread / GPU."""
+
+    def __init__(self, nsamples=5000000, fs=5e6, variant="G", modulation="bpsk", layout="interleaved2",
+                 window_hz=(-20000.0, 20000.0), freq_axis=None, nint=1, samples_per_chip=2, ddof=1,
+                 est_sub_mean=None, max_batch=4, device=0, lib=None):
+        self.lib = _lib.load(lib)
+        cfg = _lib.Config()
+        self.lib.twstft_default_config(C.byref(cfg))
+        cfg.fs = fs
+        cfg.nsamples = int(nsamples)
+        cfg.samples_per_chip = samples_per_chip
+        cfg.variant = _lib.VARIANT_K if str(variant).upper().startswith("K") else _lib.VARIANT_G
+        cfg.modulation = _lib.QPSK if str(modulation).lower() == "qpsk" else _lib.BPSK
+        cfg.nint = nint
+        cfg.layout = _lib.LAYOUT_SINGLE if layout in ("single", 1) else _lib.LAYOUT_INTERLEAVED2
+        if freq_axis is None:
+            freq_axis = "K" if cfg.variant == _lib.VARIANT_K else "G"
+        cfg.freq_axis = _lib.AXIS_K if freq_axis == "K" else _lib.AXIS_G
+        cfg.win_lo_hz, cfg.win_hi_hz = float(window_hz[0]), float(window_hz[1])
+        cfg.est_sub_mean = int(cfg.variant == _lib.VARIANT_G if est_sub_mean is None else est_sub_mean)
+        cfg.ddof = ddof
+        cfg.max_batch = max_batch
+        cfg.device_id = device
+        self.cfg = cfg
+        self.nch = 2 if cfg.layout == _lib.LAYOUT_INTERLEAVED2 else 1
+        self.N = int(nsamples)
+        self._plan = C.c_void_p()
+        rc = self.lib.twstft_plan_create(C.byref(cfg), C.byref(self._plan))
+        if rc != 0:
+            msg = self.lib.twstft_last_error(self._plan).decode() if self._plan else "plan creation failed"
+            self.close()
+            raise TwstftError(f"twstft_plan_create failed ({rc}): {msg}")
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_plan", None):
+            self.lib.twstft_plan_destroy(self._plan)
+            self._plan = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise TwstftError(f"{what} failed ({rc}): {self.lib.twstft_last_error(self._plan).decode()}")
+
+    @property
+    def backend(self):
+        return self.lib.twstft_backend().decode()
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.twstft_kernel_launches(self._plan))
+
+    def window_bins(self):
+        lo, hi = C.c_int64(), C.c_int64()
+        self.lib.twstft_window_bins(self._plan, C.byref(lo), C.byref(hi))
+        return lo.value, hi.value
+
+    # ------------------------------------------------------------------ PRN replica
+    def set_code(self, chips, qpsk=False):
+        chips = np.ascontiguousarray(chips, dtype=np.uint8)
+        self._check(self.lib.twstft_set_code(self._plan, chips.ctypes.data, chips.size, int(qpsk)), "twstft_set_code")
+
+    def gen_code(self, bitlen, taps_a, taps_b=0, seed=1, noiselen=None):
+        noiselen = int(noiselen if noiselen is not None else self.N // self.cfg.samples_per_chip)
+        out = np.empty(noiselen * (2 if taps_b else 1), dtype=np.uint8)
+        self._check(self.lib.twstft_gen_code(self._plan, bitlen, taps_a, taps_b, seed, noiselen, out.ctypes.data),
+                    "twstft_gen_code")
+        return out
+
+    # ------------------------------------------------------------------ hot path
+    def _records(self, iq):
+        iq = np.ascontiguousarray(iq, dtype=np.int16)
+        per = 2 * self.nch * self.N
+        if iq.size % per:
+            raise ValueError(f"input holds {iq.size} int16, not a multiple of one record ({per})")
+        return iq, iq.size // per
+
+    def process(self, iq):
+        """iq: int16 host array of whole records ([I1 Q1 I2 Q2]... or [I Q]...).  Returns a structured
+        array of shape (nrecords, nch)."""
+        iq, nrec = self._records(iq)
+        out = np.zeros((nrec, self.nch), dtype=RESULT_DTYPE)
+        self._check(self.lib.twstft_process(self._plan, iq.ctypes.data, nrec, out.ctypes.data), "twstft_process")
+        return out
+
+    def process_device(self, dev_ptr, nrecords):
+        out = np.zeros((nrecords, self.nch), dtype=RESULT_DTYPE)
+        self._check(self.lib.twstft_process_device(self._plan, dev_ptr, nrecords, out.ctypes.data),
+                    "twstft_process_device")
+        return out
+
+    def process_windows(self, iq, offsets, df, on_device=False, total_instants=None):
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        df = np.ascontiguousarray(np.broadcast_to(np.asarray(df, dtype=np.float64).reshape(len(offsets), -1),
+                                                  (len(offsets), self.nch)))
+        out = np.zeros((len(offsets), self.nch), dtype=RESULT_DTYPE)
+        if on_device:
+            ptr, tot = iq, int(total_instants)
+        else:
+            iq = np.ascontiguousarray(iq, dtype=np.int16)
+            ptr, tot = iq.ctypes.data, iq.size // (2 * self.nch)
+        self._check(self.lib.twstft_process_windows(self._plan, ptr, int(on_device), tot, offsets.ctypes.data,
+                                                    df.ctypes.data, len(offsets), out.ctypes.data),
+                    "twstft_process_windows")
+        return out
+
+    def estimate_carrier(self, iq):
+        iq, nrec = self._records(iq)
+        df = np.zeros((nrec, self.nch))
+        bins = np.zeros((nrec, self.nch), dtype=np.int64)
+        self._check(self.lib.twstft_estimate_carrier(self._plan, iq.ctypes.data, 0, nrec, df.ctypes.data,
+                                                     bins.ctypes.data), "twstft_estimate_carrier")
+        return df, bins
+
+    # ------------------------------------------------------------------ device memory helpers
+    def to_device(self, arr):
+        arr = np.ascontiguousarray(arr)
+        ptr = C.c_void_p()
+        self._check(self.lib.twstft_device_alloc(self._plan, arr.nbytes, C.byref(ptr)), "twstft_device_alloc")
+        self._check(self.lib.twstft_copy_to_device(self._plan, ptr, arr.ctypes.data, arr.nbytes), "twstft_copy_to_device")
+        return ptr
+
+    def device_free(self, ptr):
+        self.lib.twstft_device_free(self._plan, ptr)
+
+    def debug_fetch(self, what, lane, count, dtype):
+        out = np.zeros(count, dtype=dtype)
+        self._check(self.lib.twstft_debug_fetch(self._plan, what, lane, out.ctypes.data, out.nbytes), "twstft_debug_fetch")
+        return out
+
+
+def delay_samples(res):
+    """Printed delay of godual_ranging.m:96-98 in samples: (indice-1+correction)/3."""
+    return (res["indice"] - 1.0 + res["correction"]) / 3.0

@@ -1,0 +1,73 @@
+// Memory + launch backend used by pipeline.cuh.
+//
+// PRODUCT build (default): CUDA only -- cudaMalloc / cudaMemcpyAsync / <<<>>> launches on the
+// plan's stream.  There is NO CPU code path in the product library.
+//
+// TEST build (-DTWSTFT_EMU, only tests/emu/Makefile does that, output tests/emu/_build/): the very
+// same kernel phase functions are executed thread by thread on the host so that the CPU test-suite
+// can check every kernel's index arithmetic against the oracle without a GPU.  That library is
+// test infrastructure; amaranth_twstft_b200 never loads it.
+#pragma once
+#include "launch.cuh"
+#ifdef TWSTFT_EMU
+#include "../../tests/emu/emu_backend.h"
+#else
+#include <stdio.h>
+#include <string.h>
+
+namespace twstft {
+
+struct Backend {
+    typedef DeviceLauncher Launcher;
+    static constexpr bool is_emulation = false;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    int device = 0;
+    cudaError_t err = cudaSuccess;
+    long launches = 0;
+
+    bool ok() const { return err == cudaSuccess; }
+    void note(cudaError_t e) { if (e != cudaSuccess && err == cudaSuccess) err = e; }
+    const char* err_string() const { return cudaGetErrorString(err); }
+
+    int init(int dev)
+    {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0) { err = (e != cudaSuccess) ? e : cudaErrorNoDevice; return -1; }
+        if (dev < 0 || dev >= n) { err = cudaErrorInvalidDevice; return -1; }
+        device = dev;
+        note(cudaSetDevice(dev));
+        note(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        note(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        return ok() ? 0 : -1;
+    }
+    void shutdown()
+    {
+        if (stream) cudaStreamDestroy(stream);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        stream = copy_stream = nullptr;
+    }
+    void use() { cudaSetDevice(device); }
+    void* alloc(size_t bytes)
+    {
+        void* p = nullptr;
+        note(cudaMalloc(&p, bytes ? bytes : 1));
+        return p;
+    }
+    void free(void* p) { if (p) cudaFree(p); }
+    void zero(void* p, size_t bytes) { note(cudaMemsetAsync(p, 0, bytes, stream)); }
+    void h2d(void* d, const void* h, size_t bytes) { note(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream)); }
+    void d2h(void* h, const void* d, size_t bytes) { note(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, stream)); }
+    void sync() { note(cudaStreamSynchronize(stream)); }
+    template <class K> void launch(dim3 grid, const typename K::Params& p)
+    {
+        DeviceLauncher l{stream};
+        l.launch<K>(grid, p);
+        note(l.err);
+        launches++;
+    }
+};
+
+}  // namespace twstft
+#endif

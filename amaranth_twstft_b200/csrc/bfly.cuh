@@ -1,0 +1,99 @@
+// In-register forward DFT butterflies (W = exp(-2*pi*i/R)) for radices 2,4,5 and the composites
+// 8,10,16,20,25 built from them (Cooley-Tukey inside the register file, constant twiddles).
+// Inverse transforms reuse these through the swap(re,im) identity, see fft_core.cuh.
+#pragma once
+#include "common.cuh"
+#include "unit_roots.inc"
+
+namespace twstft {
+
+template <int R> struct Bfly;
+
+template <> struct Bfly<1> { static HD void run(float2*) {} };
+
+template <> struct Bfly<2> {
+    static HD void run(float2* v)
+    {
+        float2 a = v[0], b = v[1];
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
+    }
+};
+
+template <> struct Bfly<4> {
+    static HD void run(float2* v)
+    {
+        float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+        float2 t2 = cadd(v[1], v[3]), t3 = csub(v[1], v[3]);
+        v[0] = cadd(t0, t2);
+        v[2] = csub(t0, t2);
+        v[1] = make_float2(t1.x + t3.y, t1.y - t3.x);   // t1 - i*t3
+        v[3] = make_float2(t1.x - t3.y, t1.y + t3.x);   // t1 + i*t3
+    }
+};
+
+template <> struct Bfly<5> {
+    static HD void run(float2* v)
+    {
+        const float c1 = 0.30901699437494745f, c2 = -0.8090169943749473f;
+        const float s1 = 0.9510565162951535f, s2 = 0.5877852522924732f;
+        float2 t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]);
+        float2 t3 = csub(v[1], v[4]), t4 = csub(v[2], v[3]);
+        float2 a1 = make_float2(v[0].x + c1 * t1.x + c2 * t2.x, v[0].y + c1 * t1.y + c2 * t2.y);
+        float2 a2 = make_float2(v[0].x + c2 * t1.x + c1 * t2.x, v[0].y + c2 * t1.y + c1 * t2.y);
+        float2 b1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
+        float2 b2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
+        v[0] = make_float2(v[0].x + t1.x + t2.x, v[0].y + t1.y + t2.y);
+        v[1] = make_float2(a1.x + b1.y, a1.y - b1.x);   // a1 - i*b1
+        v[4] = make_float2(a1.x - b1.y, a1.y + b1.x);   // a1 + i*b1
+        v[2] = make_float2(a2.x + b2.y, a2.y - b2.x);
+        v[3] = make_float2(a2.x - b2.y, a2.y + b2.x);
+    }
+};
+
+// multiply by W_R^t with the trivial rotations resolved at compile time (t is a constant after unrolling)
+template <int R> HD float2 mul_root(float2 a, int t)
+{
+    t = t % R;
+    if (t == 0) return a;
+    if ((R % 4 == 0) && t == R / 4) return make_float2(a.y, -a.x);       // * (-i)
+    if ((R % 2 == 0) && t == R / 2) return make_float2(-a.x, -a.y);
+    if ((R % 4 == 0) && t == 3 * R / 4) return make_float2(-a.y, a.x);   // * (+i)
+    float c, s;
+    UnitRoots<R>::get(t, c, s);
+    return make_float2(a.x * c + a.y * s, a.y * c - a.x * s);            // a * (c - i s)
+}
+
+// R = RA*RB: n = na*RB + nb, k = ka + RA*kb
+template <int RA, int RB> struct BflyCT {
+    static HD void run(float2* v)
+    {
+        constexpr int R = RA * RB;
+#pragma unroll
+        for (int nb = 0; nb < RB; nb++) {
+            float2 t[RA];
+#pragma unroll
+            for (int na = 0; na < RA; na++) t[na] = v[na * RB + nb];
+            Bfly<RA>::run(t);
+#pragma unroll
+            for (int ka = 0; ka < RA; ka++) v[ka * RB + nb] = mul_root<R>(t[ka], nb * ka);
+        }
+#pragma unroll
+        for (int ka = 0; ka < RA; ka++) Bfly<RB>::run(v + ka * RB);
+        float2 o[R];
+#pragma unroll
+        for (int ka = 0; ka < RA; ka++)
+#pragma unroll
+            for (int kb = 0; kb < RB; kb++) o[ka + RA * kb] = v[RB * ka + kb];
+#pragma unroll
+        for (int i = 0; i < R; i++) v[i] = o[i];
+    }
+};
+
+template <> struct Bfly<8> { static HD void run(float2* v) { BflyCT<2, 4>::run(v); } };
+template <> struct Bfly<10> { static HD void run(float2* v) { BflyCT<2, 5>::run(v); } };
+template <> struct Bfly<16> { static HD void run(float2* v) { BflyCT<4, 4>::run(v); } };
+template <> struct Bfly<20> { static HD void run(float2* v) { BflyCT<4, 5>::run(v); } };
+template <> struct Bfly<25> { static HD void run(float2* v) { BflyCT<5, 5>::run(v); } };
+
+}  // namespace twstft

@@ -1,0 +1,96 @@
+// Common definitions for the B200 PRN correlator kernels.
+//
+// Every kernel is written as a struct of per-thread "phases" (__host__ __device__), separated by
+// block-wide barriers or block reductions.  On the GPU the phases run inside one __global__
+// kernel (launch.cuh).  The same phase functions are also compiled for the host by the TEST-ONLY
+// emulator (tests/emu), which runs them thread by thread so the index arithmetic of every kernel
+// can be checked against the oracle in the CPU test-suite.  The emulator is never part of the
+// product library.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+#include <math.h>
+#include <cuda_runtime.h>
+
+#define HD __host__ __device__ __forceinline__
+
+namespace twstft {
+
+typedef unsigned long long u64;
+typedef long long i64;
+
+struct Blk { int x, y, z; };
+
+enum SyncKind { SYNC_BARRIER = 0, SYNC_MAXKEY = 1, SYNC_SUMD = 2, SYNC_MAXKEY_SUMD = 3 };
+
+// ------------------------------------------------------------------ complex fp32 helpers
+HD float2 cf(float x, float y) { return make_float2(x, y); }
+HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+HD float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a*conj(b)
+HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+HD float2 cswap(float2 a) { return make_float2(a.y, a.x); }
+HD float cnorm(float2 a) { return a.x * a.x + a.y * a.y; }
+
+// exp(2*pi*i*cycles) in fp32, phase reduced in fp64 so that the fp32 argument is < 1/8 turn.
+HD float2 cis_cycles(double c)
+{
+    c -= rint(c);
+    double c4 = c * 4.0;
+    double q = rint(c4);
+    float r = (float)((c4 - q) * 0.25);  // |r| <= 1/8 cycle
+    int qi = ((int)q) & 3;
+    float s, co;
+#ifdef __CUDA_ARCH__
+    sincospif(2.0f * r, &s, &co);
+#else
+    s = (float)sin(6.283185307179586476925287 * (double)r);
+    co = (float)cos(6.283185307179586476925287 * (double)r);
+#endif
+    float2 w;
+    if (qi == 0) w = make_float2(co, s);
+    else if (qi == 1) w = make_float2(-s, co);
+    else if (qi == 2) w = make_float2(-co, -s);
+    else w = make_float2(s, -co);
+    return w;
+}
+
+// exp(2*pi*i*cycles) in fp64.
+HD double2 cis_cycles_d(double c)
+{
+    c -= rint(c);
+    double s, co;
+#ifdef __CUDA_ARCH__
+    sincospi(2.0 * c, &s, &co);
+#else
+    s = sin(6.283185307179586476925287 * c);
+    co = cos(6.283185307179586476925287 * c);
+#endif
+    return make_double2(co, s);
+}
+
+HD double2 dmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// Order-preserving key for "first maximum": larger value wins, then SMALLER index.
+HD u64 make_key(float v, unsigned idx)
+{
+#ifdef __CUDA_ARCH__
+    unsigned b = __float_as_uint(v);
+#else
+    union { float f; unsigned u; } cv; cv.f = v; unsigned b = cv.u;
+#endif
+    return ((u64)b << 32) | (u64)(0xFFFFFFFFu - idx);   // v >= 0 so the bit pattern is monotone
+}
+HD unsigned key_index(u64 k) { return 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull); }
+HD float key_value(u64 k)
+{
+    unsigned b = (unsigned)(k >> 32);
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    union { float f; unsigned u; } cv; cv.u = b; return cv.f;
+#endif
+}
+
+}  // namespace twstft

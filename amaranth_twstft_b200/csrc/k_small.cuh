@@ -1,0 +1,418 @@
+// Small kernels around the FFT passes: window mean, carrier-offset finalisation (+ derotation
+// tables), peak refinement (exact fp64 evaluation of the interpolated correlation around the coarse
+// maximum), parabolic fine delay, phase and the "Claudio" SNR, and the LFSR PRN generator.
+#pragma once
+#include "fft_core.cuh"
+
+namespace twstft {
+
+HD void atomic_add_d(double* p, double v)
+{
+#ifdef __CUDA_ARCH__
+    atomicAdd(p, v);
+#else
+    *p += v;
+#endif
+}
+HD double mul_rn(double a, double b)
+{
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    volatile double r = a * b;
+    return r;
+#endif
+}
+HD double add_rn(double a, double b)
+{
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b;
+    return r;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// KMean: exact sums of I and Q over each window (godual_ranging.m:80 d1=d1-mean(d1); the means are
+// applied inside the column pass).  Sums of int16 over <= 1e7 samples stay below 2^53, so double
+// accumulation (and double atomics, in any order) is exact.
+struct MeanParams {
+    const short2* src;
+    i64 nelem;             // complex-int16 elements in the window, all channels (= N * nch)
+    int nch;
+    i64 rec_stride;
+    const i64* rec_offset;
+    double* sums;          // [record*nch + ch][2], zeroed by the caller
+    int nblk;
+};
+struct KMean {
+    typedef MeanParams Params;
+    static constexpr int NT = 256, MINB = 4, NPH = 2, NSUM = 4;
+    struct Regs { u64 key; double dsum[NSUM]; };
+    static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }
+    static HD constexpr int sync_after(int) { return SYNC_SUMD; }
+    template <int PH> static HD void phase(const Params& p, const Blk& blk, int tid, Regs& r, unsigned char*)
+    {
+        if (PH == 0) {
+            const i64 base = p.rec_offset ? p.rec_offset[blk.y] : (i64)blk.y * p.rec_stride;
+            const short2* s = p.src + base;
+            const i64 stride = (i64)p.nblk * NT;      // even, so a thread always sees the same channel
+            i64 sx = 0, sy = 0;
+            const i64 e0 = (i64)blk.x * NT + tid;
+#pragma unroll 4
+            for (i64 e = e0; e < p.nelem; e += stride) {
+                const short2 v = s[e];
+                sx += v.x;
+                sy += v.y;
+            }
+            const int ch = (int)(e0 % p.nch);
+            r.dsum[0] = ch == 0 ? (double)sx : 0.0;
+            r.dsum[1] = ch == 0 ? (double)sy : 0.0;
+            r.dsum[2] = ch == 1 ? (double)sx : 0.0;
+            r.dsum[3] = ch == 1 ? (double)sy : 0.0;
+        } else if (tid == 0) {
+            double* o = p.sums + (i64)blk.y * p.nch * 2;
+            atomic_add_d(o + 0, r.dsum[0]);
+            atomic_add_d(o + 1, r.dsum[1]);
+            if (p.nch > 1) {
+                atomic_add_d(o + 2, r.dsum[2]);
+                atomic_add_d(o + 3, r.dsum[3]);
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// KDfFinal: reduce the per-row window maxima of the |fft(x^p)| spectrum to the carrier bin,
+// df = freq(s)/p with the reference's inclusive linspace axis (godual_ranging.m:15,73 -- the
+// "+0.25 Hz" grid quirk; claudio_aligned_code_lo_separate.m:103,129), then build the two-level
+// derotation tables exp(-j2pi df n/fs), n = n1*N2 + n2  (godual_ranging.m:17).
+struct DfParams {
+    const u64* part_key;   // [lane][npart]
+    int npart;
+    const double* df_in;   // optional [lane]: skip the estimator (variant K processing(d,k,df))
+    double f0, fstep, flast;   // linspace(start, stop, n): start + s*step, last point = stop exactly
+    i64 naxis;
+    double power;          // 2 (BPSK) or 4 (QPSK)
+    double fs;
+    int L1, N2;
+    double* df_out;        // [lane]
+    i64* s_out;            // [lane] index into the fftshift'ed axis (-1 when df_in is used)
+    float2* lrow;          // [lane][L1]
+    float2* lcol;          // [lane][N2]
+    int nsplit;
+};
+struct KDfFinal {
+    typedef DfParams Params;
+    static constexpr int NT = 256, MINB = 4, NPH = 2, NSUM = 1;
+    struct Regs { u64 key; double dsum[NSUM]; };
+    static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }
+    static HD constexpr int sync_after(int) { return SYNC_MAXKEY; }
+    template <int PH> static HD void phase(const Params& p, const Blk& blk, int tid, Regs& r, unsigned char*)
+    {
+        const i64 lane = blk.y;
+        if (PH == 0) {
+            u64 best = 0;
+            if (!p.df_in)
+                for (int i = tid; i < p.npart; i += NT) {
+                    const u64 k = p.part_key[lane * p.npart + i];
+                    best = k > best ? k : best;
+                }
+            r.key = best;
+            r.dsum[0] = 0.0;
+        } else {
+            double df;
+            i64 s = -1;
+            if (p.df_in) df = p.df_in[lane];
+            else {
+                s = (i64)key_index(r.key);
+                const double f = (s == p.naxis - 1) ? p.flast : add_rn(mul_rn((double)s, p.fstep), p.f0);
+                df = f / p.power;
+            }
+            if (blk.x == 0 && tid == 0) {
+                p.df_out[lane] = df;
+                p.s_out[lane] = s;
+            }
+            const int tot = p.L1 + p.N2;
+            for (int e = blk.x * NT + tid; e < tot; e += p.nsplit * NT) {
+                if (e < p.L1) p.lrow[lane * p.L1 + e] = cis_cycles(-df * ((double)((i64)e * p.N2) / p.fs));
+                else p.lcol[lane * p.N2 + (e - p.L1)] = cis_cycles(-df * ((double)(e - p.L1) / p.fs));
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Peak refinement.  With P the (transposed-order) product spectrum, the interpolated correlation is
+//   prnmap[p] = (1/M) sum_k P[k] exp(2 pi i ktilde p / M),  M = nq*N, ktilde = k - N for k >= N/2
+// (godual_ranging.m:26-28).  Around the coarse maximum p0 found by the fp32 inverse FFT we evaluate
+// NPTS points p0+DLO .. p0+DLO+NPTS-1 exactly (fp64 accumulation, fp64 phase reduction):
+//   k = k1 + L1*k2  ->  exp(..) = rowph[d][k1] * wk2[d][k2]
+constexpr int PEAK_NPTS = 7;
+constexpr int PEAK_DLO = -4;
+
+struct PeakTabParams {
+    const u64* part_key;   // [lane][npart]
+    int npart;
+    i64 N;
+    int nq;
+    int L1, N2;
+    i64* p0_out;           // [lane]
+    float2* rowph;         // [lane][NPTS][L1]
+    float2* wk2;           // [lane][NPTS][N2]
+    int nsplit;
+};
+struct KPeakTables {
+    typedef PeakTabParams Params;
+    static constexpr int NT = 256, MINB = 4, NPH = 2, NSUM = 1;
+    struct Regs { u64 key; double dsum[NSUM]; };
+    static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }
+    static HD constexpr int sync_after(int) { return SYNC_MAXKEY; }
+    template <int PH> static HD void phase(const Params& p, const Blk& blk, int tid, Regs& r, unsigned char*)
+    {
+        const i64 lane = blk.y;
+        if (PH == 0) {
+            u64 best = 0;
+            for (int i = tid; i < p.npart; i += NT) {
+                const u64 k = p.part_key[lane * p.npart + i];
+                best = k > best ? k : best;
+            }
+            r.key = best;
+            r.dsum[0] = 0.0;
+        } else {
+            const i64 M = (i64)p.nq * p.N;
+            const i64 p0 = (i64)key_index(r.key);
+            if (blk.x == 0 && tid == 0) p.p0_out[lane] = p0;
+            const int per = p.L1 + p.N2;
+            const int tot = PEAK_NPTS * per;
+            const double invM = 1.0 / (double)M;
+            for (int e = blk.x * NT + tid; e < tot; e += p.nsplit * NT) {
+                const int d = e / per, rr = e % per;
+                i64 pp = (p0 + PEAK_DLO + d) % M;
+                if (pp < 0) pp += M;
+                if (rr < p.L1) {
+                    const i64 x = ((i64)rr * pp) % M;
+                    p.rowph[(lane * PEAK_NPTS + d) * p.L1 + rr] = cis_cycles((double)x * invM);
+                } else {
+                    const int k2 = rr - p.L1;
+                    const i64 x = (((i64)p.L1 * k2) % M * pp) % M;
+                    double c = (double)x * invM;
+                    if (k2 >= p.N2 / 2) c -= (double)((p.N % M) * pp % M) * invM;
+                    p.wk2[(lane * PEAK_NPTS + d) * p.N2 + k2] = cis_cycles(c);
+                }
+            }
+        }
+    }
+};
+
+struct PeakSumParams {
+    const float2* P;       // [lane][N]
+    const float2* rowph;   // [lane][NPTS][L1]
+    const float2* wk2;     // [lane][NPTS][N2]
+    i64 N;
+    int L1, N2;
+    double* part;          // [lane][nblk][2*NPTS]
+    int nblk;
+};
+template <int L1MAX> struct KPeakSums {
+    typedef PeakSumParams Params;
+    static constexpr int KW = 16;                 // k2 columns per CTA
+    static constexpr int NT = 256, MINB = 2, NPH = 3, NSUM = 2 * PEAK_NPTS;
+    static constexpr int NGRP = NT / KW;
+    struct Regs { u64 key; double dsum[NSUM]; };
+    static HD constexpr size_t smem_bytes() { return (size_t)PEAK_NPTS * L1MAX * sizeof(float2) + RED_SCRATCH_BYTES; }
+    static HD constexpr int sync_after(int ph) { return ph == 0 ? SYNC_BARRIER : SYNC_SUMD; }
+    template <int PH> static HD void phase(const Params& p, const Blk& blk, int tid, Regs& r, unsigned char* smem)
+    {
+        float2* rp = reinterpret_cast<float2*>(smem);
+        const i64 lane = blk.y;
+        if (PH == 0) {
+            const float2* src = p.rowph + lane * PEAK_NPTS * p.L1;
+            for (int i = tid; i < PEAK_NPTS * p.L1; i += NT) rp[i] = src[i];
+        } else if (PH == 1) {
+            const int kl = tid % KW, g = tid / KW;
+            const int k2 = blk.x * KW + kl;
+            const float2* src = p.P + lane * p.N + k2;
+            float2 acc[PEAK_NPTS];
+#pragma unroll
+            for (int d = 0; d < PEAK_NPTS; d++) acc[d] = make_float2(0.f, 0.f);
+#pragma unroll 4
+            for (int k1 = g; k1 < p.L1; k1 += NGRP) {
+                const float2 x = src[(i64)k1 * p.N2];
+#pragma unroll
+                for (int d = 0; d < PEAK_NPTS; d++) {
+                    const float2 w = rp[d * p.L1 + k1];
+                    acc[d].x += x.x * w.x - x.y * w.y;
+                    acc[d].y += x.x * w.y + x.y * w.x;
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < PEAK_NPTS; d++) {
+                const float2 w = p.wk2[(lane * PEAK_NPTS + d) * p.N2 + k2];
+                r.dsum[2 * d] = (double)acc[d].x * (double)w.x - (double)acc[d].y * (double)w.y;
+                r.dsum[2 * d + 1] = (double)acc[d].x * (double)w.y + (double)acc[d].y * (double)w.x;
+            }
+        } else if (tid == 0) {
+            double* o = p.part + (lane * p.nblk + blk.x) * NSUM;
+#pragma unroll
+            for (int i = 0; i < NSUM; i++) o[i] = r.dsum[i];
+        }
+    }
+};
+
+// One result row per lane = one row of the reference's .mat variables.
+struct Result {
+    double indice;          // 1-based index on the interpolated grid (Octave convention)
+    double correction;      // parabolic vertex offset, interpolated-grid units
+    double xval_re, xval_im, xvalm1_re, xvalm1_im, xvalp1_re, xvalp1_im;
+    double SNRr, SNRi;
+    double df;
+    double puissance, puissancecode, puissancenoise;
+    double carrier_bin;     // 0-based index into the fftshift'ed estimator axis (-1: df was given)
+    double status;          // bit0: peak at an edge (reference would index out of range), bit1: refined peak moved
+};
+constexpr int RESULT_NDOUBLE = sizeof(Result) / sizeof(double);
+
+struct PeakFinParams {
+    const double* part;        // [lane][nblk][2*NPTS]
+    int nblk;
+    const double* part_energy; // [lane][nen]
+    int nen;
+    const float2* y0;          // [lane]
+    const i64* p0;             // [lane]
+    const double* df;          // [lane]
+    const i64* sbin;           // [lane]
+    i64 N;
+    int nq;
+    int variant;               // 0 = G (godual_ranging.m), 1 = K (claudio_aligned_code_*_separate.m)
+    int ddof;                  // 1 = Octave var, 0 = numpy var
+    Result* out;               // [lane]
+};
+struct KPeakFinal {
+    typedef PeakFinParams Params;
+    static constexpr int NT = 256, MINB = 4, NPH = 2, NSUM = 2 * PEAK_NPTS + 1;
+    struct Regs { u64 key; double dsum[NSUM]; };
+    static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }
+    static HD constexpr int sync_after(int) { return SYNC_SUMD; }
+    template <int PH> static HD void phase(const Params& p, const Blk& blk, int tid, Regs& r, unsigned char*)
+    {
+        const i64 lane = blk.y;
+        if (PH == 0) {
+#pragma unroll
+            for (int i = 0; i < NSUM; i++) r.dsum[i] = 0.0;
+            for (int b = tid; b < p.nblk; b += NT) {
+                const double* s = p.part + (lane * p.nblk + b) * (2 * PEAK_NPTS);
+#pragma unroll
+                for (int i = 0; i < 2 * PEAK_NPTS; i++) r.dsum[i] += s[i];
+            }
+            for (int b = tid; b < p.nen; b += NT) r.dsum[2 * PEAK_NPTS] += p.part_energy[lane * p.nen + b];
+            return;
+        }
+        if (tid != 0) return;
+        const i64 M = (i64)p.nq * p.N;
+        const double invM = 1.0 / (double)M;
+        double sr[PEAK_NPTS], si[PEAK_NPTS], a2[PEAK_NPTS];
+#pragma unroll
+        for (int d = 0; d < PEAK_NPTS; d++) {
+            sr[d] = r.dsum[2 * d] * invM;
+            si[d] = r.dsum[2 * d + 1] * invM;
+            a2[d] = sr[d] * sr[d] + si[d] * si[d];
+        }
+        const i64 p0 = p.p0[lane];
+        // fp64 re-decision among p0-1, p0, p0+1 with first-max semantics on the (wrapped) index
+        const int c0 = -PEAK_DLO;
+        int c = c0;
+        i64 pc = p0;
+        for (int t = -1; t <= 1; t += 2) {
+            i64 pt = (p0 + t) % M;
+            if (pt < 0) pt += M;
+            const int ct = c0 + t;
+            if (a2[ct] > a2[c] || (a2[ct] == a2[c] && pt < pc)) { c = ct; pc = pt; }
+        }
+        double status = (c != c0) ? 2.0 : 0.0;
+        const double am1 = sqrt(a2[c - 1]), a0 = sqrt(a2[c]);
+        int cp = c + 1;
+        if (p.variant == 1 && pc == M - 2) cp = c + 2;     // lo_separate.m:51-55 strict '<' quirk
+        if (cp >= PEAK_NPTS) { cp = PEAK_NPTS - 1; status += 1.0; }
+        if (p.variant == 0 && (pc == 0 || pc == M - 1)) status += 1.0;   // Octave would index out of range
+        const double ap1 = sqrt(a2[cp]);
+        Result o;
+        o.indice = (double)(pc + 1);
+        o.correction = (am1 - ap1) / (am1 + ap1 - 2.0 * a0) / 2.0;
+        o.xval_re = sr[c]; o.xval_im = si[c];
+        o.xvalm1_re = sr[c - 1]; o.xvalm1_im = si[c - 1];
+        o.xvalp1_re = sr[cp]; o.xvalp1_im = si[cp];
+        // "Claudio" SNR through the spectral identity: the mean of yincode is the sum of
+        // three adjacent correlation lags / M; sum|yint|^2 follows from Parseval.
+        double mr, mi;
+        if (p.variant == 0) {            // godual_ranging.m:43 rotate the signal by indice-2
+            mr = (sr[c - 1] + sr[c] + sr[c + 1 < PEAK_NPTS ? c + 1 : c]) * invM;
+            mi = (si[c - 1] + si[c] + si[c + 1 < PEAK_NPTS ? c + 1 : c]) * invM;
+        } else {                         // lo_separate.m:65-69 rotate the code by indice-2 when indice>2
+            const int a = (pc == 0) ? c : c - 1;
+            mr = (sr[a] + sr[a - 1] + sr[a - 2]) * invM;
+            mi = -(si[a] + si[a - 1] + si[a - 2]) * invM;
+        }
+        const double E = r.dsum[2 * PEAK_NPTS];
+        const double n = (double)p.N, m = (double)M;
+        const double var_c = (E / m - m * (mr * mr + mi * mi)) / (m - (double)p.ddof);
+        const float2 y0 = p.y0[lane];
+        const double y0n = (double)y0.x * (double)y0.x + (double)y0.y * (double)y0.y;
+        o.SNRr = mr * mr / var_c;
+        o.SNRi = mi * mi / var_c;
+        o.df = p.df[lane];
+        o.puissance = (E / n - y0n / n) / (n - (double)p.ddof);
+        o.puissancecode = mr * mr + mi * mi;
+        o.puissancenoise = var_c;
+        o.carrier_bin = (double)p.sbin[lane];
+        o.status = status;
+        p.out[lane] = o;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// KPrnGen: LFSR PRN replica (amaranth_twstft/common.py:23-30,59-73; prn.py:43-51).  Every thread
+// jumps to chip t0 = gid*CH with the precomputed GF(2) powers M^(2^j) of the one-step matrix
+// (columns as bit masks), then steps CH chips emitting the LSB before each step.
+struct PrnParams {
+    unsigned jump[24][24];   // jump[j][i] = column i of M^(2^j)
+    int bitlen;
+    unsigned taps, seed;
+    i64 nchips;
+    unsigned char* out;
+    int ostride, ooffset;    // out[ostride*i + ooffset]  (QPSK: stride 2, offset 0/1)
+};
+struct KPrnGen {
+    typedef PrnParams Params;
+    static constexpr int NT = 128, MINB = 4, NPH = 1, NSUM = 1, CH = 64;
+    struct Regs { u64 key; double dsum[NSUM]; };
+    static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }
+    static HD constexpr int sync_after(int) { return SYNC_BARRIER; }
+    static HD unsigned parity(unsigned x)
+    {
+        x ^= x >> 16; x ^= x >> 8; x ^= x >> 4; x ^= x >> 2; x ^= x >> 1;
+        return x & 1u;
+    }
+    template <int PH> static HD void phase(const Params& p, const Blk& blk, int tid, Regs&, unsigned char*)
+    {
+        const i64 t0 = ((i64)blk.x * NT + tid) * CH;
+        if (t0 >= p.nchips) return;
+        unsigned s = p.seed;
+        for (int j = 0; j < 24; j++)
+            if ((t0 >> j) & 1) {
+                unsigned ns = 0;
+                for (int i = 0; i < p.bitlen; i++)
+                    if ((s >> i) & 1) ns ^= p.jump[j][i];
+                s = ns;
+            }
+        const i64 tend = (t0 + CH < p.nchips) ? t0 + CH : p.nchips;
+        for (i64 t = t0; t < tend; t++) {
+            p.out[t * p.ostride + p.ooffset] = (unsigned char)(s & 1u);
+            const unsigned bit = parity(s & p.taps);
+            s = (s >> 1) | (bit << (p.bitlen - 1));
+        }
+    }
+};
+
+}  // namespace twstft

@@ -1,0 +1,104 @@
+// Generic __global__ entry for phase-structured kernels and the block-wide reductions that separate
+// their phases.  A kernel struct K provides:
+//   K::Params, K::Regs, K::NT (threads per CTA), K::MINB (min CTAs/SM), K::NPH (phase count),
+//   K::smem_bytes(), template<int PH> K::phase(p, blk, tid, regs, smem), K::sync_after(ph)
+// SYNC_MAXKEY  : regs.key   <- max over the CTA (valid in every thread afterwards)
+// SYNC_SUMD    : regs.dsum[i] <- sum over the CTA for i < K::NSUM (valid in thread 0)
+#pragma once
+#include "common.cuh"
+
+namespace twstft {
+
+constexpr int RED_SCRATCH_BYTES = 32 * 8 * 16;   // 32 warps x up to 16 doubles
+
+#ifdef __CUDACC__
+template <class K> __device__ __forceinline__ void block_max_key(typename K::Regs& r, unsigned char* scratch)
+{
+    u64 k = r.key;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        u64 other = __shfl_xor_sync(0xffffffffu, k, o);
+        k = other > k ? other : k;
+    }
+    u64* s = reinterpret_cast<u64*>(scratch);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NW = (K::NT + 31) / 32;
+    __syncthreads();                 // scratch may still be read from a previous reduction
+    if (lane == 0) s[warp] = k;
+    __syncthreads();
+    u64 best = s[0];
+#pragma unroll 1
+    for (int w = 1; w < NW; w++) best = s[w] > best ? s[w] : best;
+    r.key = best;
+}
+
+template <class K> __device__ __forceinline__ void block_sum_d(typename K::Regs& r, unsigned char* scratch)
+{
+    double* s = reinterpret_cast<double*>(scratch);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NW = (K::NT + 31) / 32;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < K::NSUM; i++) {
+        double x = r.dsum[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) s[i * 32 + warp] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < K::NSUM; i++) {
+            double t = 0.0;
+            for (int w = 0; w < NW; w++) t += s[i * 32 + w];
+            r.dsum[i] = t;
+        }
+    }
+}
+
+template <class K, int PH>
+__device__ __forceinline__ void run_phases(const typename K::Params& p, const Blk& b, int tid,
+                                           typename K::Regs& r, unsigned char* smem)
+{
+    K::template phase<PH>(p, b, tid, r, smem);
+    if constexpr (PH + 1 < K::NPH) {
+        constexpr int kind = K::sync_after(PH);
+        unsigned char* scratch = smem + K::smem_bytes() - RED_SCRATCH_BYTES;
+        if constexpr (kind == SYNC_BARRIER) __syncthreads();
+        if constexpr (kind == SYNC_MAXKEY || kind == SYNC_MAXKEY_SUMD) block_max_key<K>(r, scratch);
+        if constexpr (kind == SYNC_SUMD || kind == SYNC_MAXKEY_SUMD) block_sum_d<K>(r, scratch);
+        run_phases<K, PH + 1>(p, b, tid, r, smem);
+    }
+}
+
+template <class K> __global__ void __launch_bounds__(K::NT, K::MINB) kernel_entry(const typename K::Params p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    typename K::Regs r;
+    Blk b{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z};
+    run_phases<K, 0>(p, b, (int)threadIdx.x, r, smem);
+}
+
+// Device launcher: used by the product library.
+struct DeviceLauncher {
+    cudaStream_t stream;
+    mutable cudaError_t err = cudaSuccess;
+    mutable long launches = 0;
+    template <class K> void launch(dim3 grid, const typename K::Params& p) const
+    {
+        static bool configured[64] = {};    // per kernel type and device
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!configured[dev & 63]) {
+            cudaFuncSetAttribute(kernel_entry<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::smem_bytes());
+            configured[dev & 63] = true;
+        }
+        kernel_entry<K><<<grid, K::NT, K::smem_bytes(), stream>>>(p);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess && err == cudaSuccess) err = e;
+        launches++;
+    }
+};
+#endif  // __CUDACC__
+
+}  // namespace twstft

@@ -1,0 +1,271 @@
+// Launch sequence of the per-record correlator (one "lane" = one channel of one record/window).
+//
+//   KMean                       exact window means                          godual_ranging.m:80,94
+//   KCol<RAW,FWD>(x^p) + KRow<FWD_ARGMAX> + KDfFinal   carrier offset       godual_ranging.m:14-15
+//   KCol<RAW,FWD>(derotate) + KRow<FWD_MULCODE>        P = fft(y).*fcode    godual_ranging.m:17-26
+//   KRow<INV_TWIST> x nq + KCol<CF32,INV_ARGMAX>       x3 ifft + coarse max godual_ranging.m:27-29
+//   KPeakTables + KPeakSums + KPeakFinal                parabola, phase, SNR godual_ranging.m:30-48
+//
+// The same code drives the CUDA backend (product) and the host emulation backend (tests only).
+#pragma once
+#include <vector>
+#include <math.h>
+#include "backend.cuh"
+#include "k_row.cuh"
+#include "k_col.cuh"
+#include "k_small.cuh"
+
+namespace twstft {
+
+struct EstimatorCfg {
+    double f0, fstep, flast;   // frequency axis linspace(start, stop, naxis)
+    i64 naxis;
+    i64 win_lo, win_hi;        // inclusive window on the fftshift'ed axis
+    int power;                 // 2 or 4
+    int sub_mean;              // 1: square the mean-removed window (G), 0: raw (K)
+};
+
+struct RunArgs {
+    const short2* d_raw;
+    int nrec;
+    int nch;
+    i64 rec_stride;            // complex-int16 elements between records
+    const i64* d_rec_offset;   // optional device array [nrec]
+    int estimate;              // run the x^p carrier estimator
+    const double* d_df_in;     // [lanes] when !estimate
+    int variant;               // 0 G, 1 K
+    int ddof;
+    double fs;
+    Result* d_out;             // [lanes]
+};
+
+class IPipe {
+public:
+    virtual ~IPipe() {}
+    virtual i64 size() const = 0;
+    virtual int col_len() const = 0;
+    virtual int row_len() const = 0;
+    virtual size_t bytes_per_lane() const = 0;
+    virtual int setup(Backend* be, int max_lanes, int nq) = 0;
+    virtual int build_code(const unsigned char* d_bits, int rep, int qpsk, float2 mean) = 0;
+    virtual int estimate(const RunArgs& a, const EstimatorCfg& e) = 0;   // -> d_df/d_sbin (+ derotation tables)
+    virtual int correlate(const RunArgs& a) = 0;
+    virtual int debug_fetch(int what, int lane, void* host_out, size_t bytes) = 0;
+};
+
+template <class CS, class RS, int RPC, int TS> class Pipe : public IPipe {
+public:
+    static constexpr i64 N = (i64)CS::L * RS::L;
+    static constexpr int L1 = CS::L, N2 = RS::L;
+    static_assert(N2 % TS == 0 && (2 * N2) % TS == 0, "column tile must divide the row length");
+    static_assert(L1 % RPC == 0, "rows per CTA must divide the column length");
+    static_assert(N2 % 16 == 0, "peak-sum tile");
+    static_assert(N2 % 2 == 0, "negative-frequency split needs an even row length");
+
+    Backend* be = nullptr;
+    int max_lanes = 0, nq = 3;
+    bool have_means = false;   // estimate() already left the window means in d_sums
+    float2 *d_blob_c = nullptr, *d_blob_r = nullptr, *d_code = nullptr, *d_twq = nullptr;
+    float2 *d_A = nullptr, *d_P = nullptr, *d_B = nullptr;
+    double *d_sums = nullptr, *d_energy = nullptr, *d_df = nullptr, *d_peakpart = nullptr;
+    u64 *d_keyrow = nullptr, *d_keycol = nullptr;
+    i64 *d_sbin = nullptr, *d_p0 = nullptr;
+    float2 *d_y0 = nullptr, *d_lrow = nullptr, *d_lcol = nullptr, *d_rowph = nullptr, *d_wk2 = nullptr;
+    static constexpr int NROWBLK = L1 / RPC;
+    static constexpr int NCOLTILE = N2 / TS;
+    static constexpr int NPEAKBLK = N2 / 16;
+
+    ~Pipe() override
+    {
+        if (!be) return;
+        void* all[] = {d_blob_c, d_blob_r, d_code, d_twq, d_A, d_P, d_B, d_sums, d_energy, d_df, d_peakpart,
+                       d_keyrow, d_keycol, d_sbin, d_p0, d_y0, d_lrow, d_lcol, d_rowph, d_wk2};
+        for (void* p : all) be->free(p);
+    }
+    i64 size() const override { return N; }
+    int col_len() const override { return L1; }
+    int row_len() const override { return N2; }
+    size_t bytes_per_lane() const override { return (size_t)N * sizeof(float2) * (2 + nq); }
+
+    template <class T> T* dalloc(size_t n) { return reinterpret_cast<T*>(be->alloc(n * sizeof(T))); }
+
+    int setup(Backend* b, int lanes, int nq_) override
+    {
+        be = b;
+        max_lanes = lanes;
+        nq = nq_;
+        std::vector<float2> blob(CS::BLOB + RS::BLOB + 4);
+        d_blob_c = dalloc<float2>(CS::BLOB + 1);
+        d_blob_r = dalloc<float2>(RS::BLOB + 1);
+        fill_blob<CS>(blob.data());
+        be->h2d(d_blob_c, blob.data(), CS::BLOB * sizeof(float2));
+        be->sync();
+        fill_blob<RS>(blob.data());
+        be->h2d(d_blob_r, blob.data(), RS::BLOB * sizeof(float2));
+        be->sync();
+        // per-k2 twist of polyphase q: exp(2 pi i q ktilde/(nq N)) without the per-row factor
+        std::vector<float2> tw((size_t)nq * N2);
+        const double TWO_PI = 6.283185307179586476925287;
+        for (int q = 0; q < nq; q++)
+            for (int k2 = 0; k2 < N2; k2++) {
+                double kt = (double)L1 * k2 - (k2 >= N2 / 2 ? (double)N : 0.0);
+                double a = TWO_PI * fmod((double)q * kt / ((double)nq * (double)N), 1.0);
+                tw[(size_t)q * N2 + k2] = make_float2((float)cos(a), (float)sin(a));
+            }
+        d_twq = dalloc<float2>((size_t)nq * N2);
+        be->h2d(d_twq, tw.data(), tw.size() * sizeof(float2));
+        be->sync();
+        d_code = dalloc<float2>(N);
+        d_A = dalloc<float2>((size_t)lanes * N);
+        d_P = dalloc<float2>((size_t)lanes * N);
+        d_B = dalloc<float2>((size_t)lanes * nq * N);
+        d_sums = dalloc<double>((size_t)lanes * 2);
+        d_energy = dalloc<double>((size_t)lanes * NROWBLK);
+        d_df = dalloc<double>(lanes);
+        d_peakpart = dalloc<double>((size_t)lanes * NPEAKBLK * 2 * PEAK_NPTS);
+        d_keyrow = dalloc<u64>((size_t)lanes * NROWBLK);
+        d_keycol = dalloc<u64>((size_t)lanes * nq * NCOLTILE);
+        d_sbin = dalloc<i64>(lanes);
+        d_p0 = dalloc<i64>(lanes);
+        d_y0 = dalloc<float2>(lanes);
+        d_lrow = dalloc<float2>((size_t)lanes * L1);
+        d_lcol = dalloc<float2>((size_t)lanes * N2);
+        d_rowph = dalloc<float2>((size_t)lanes * PEAK_NPTS * L1);
+        d_wk2 = dalloc<float2>((size_t)lanes * PEAK_NPTS * N2);
+        return be->ok() ? 0 : -1;
+    }
+
+    int build_code(const unsigned char* d_bits, int rep, int qpsk, float2 mean) override
+    {
+        ColParams c{};
+        c.src = d_bits; c.dst = d_A; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.nch = 1;
+        c.rep = rep; c.qpsk = qpsk; c.code_mean = mean; c.nq = 1;
+        be->template launch<KCol<CS, TS, SRC_BITS, COL_FWD>>(dim3(NCOLTILE, 1, 1), c);
+        RowParams r{};
+        r.src = d_A; r.dst = d_code; r.blob = d_blob_r; r.N = N; r.N1 = L1; r.nq = 1; r.nblk = NROWBLK;
+        be->template launch<KRow<RS, RPC, ROW_FWD_STORE>>(dim3(NROWBLK, 1, 1), r);
+        return be->ok() ? 0 : -1;
+    }
+
+    void means(const RunArgs& a)
+    {
+        const int lanes = a.nrec * a.nch;
+        be->zero(d_sums, (size_t)lanes * 2 * sizeof(double));
+        MeanParams m{};
+        m.src = a.d_raw; m.nelem = N * a.nch; m.nch = a.nch; m.rec_stride = a.rec_stride;
+        m.rec_offset = a.d_rec_offset; m.sums = d_sums;
+        i64 per = (m.nelem + KMean::NT - 1) / KMean::NT;
+        int nblk = (int)(per < 592 ? (per < 1 ? 1 : per) : 592);
+        m.nblk = nblk;
+        be->template launch<KMean>(dim3(nblk, a.nrec, 1), m);
+    }
+
+    void col_raw(const RunArgs& a, int op, int sub_mean)
+    {
+        ColParams c{};
+        c.src = a.d_raw; c.dst = d_A; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.nch = a.nch;
+        c.op = op; c.sub_mean = sub_mean; c.sums = d_sums; c.lrow = d_lrow; c.lcol = d_lcol;
+        c.rec_stride = a.rec_stride; c.rec_offset = a.d_rec_offset; c.nq = 1;
+        be->template launch<KCol<CS, TS, SRC_RAW, COL_FWD>>(dim3(NCOLTILE * a.nch, a.nrec, 1), c);
+    }
+
+    void df_final(const RunArgs& a, const EstimatorCfg* e)
+    {
+        const int lanes = a.nrec * a.nch;
+        DfParams d{};
+        d.part_key = d_keyrow; d.npart = NROWBLK; d.df_in = e ? nullptr : a.d_df_in;
+        if (e) { d.f0 = e->f0; d.fstep = e->fstep; d.flast = e->flast; d.naxis = e->naxis; d.power = (double)e->power; }
+        else { d.power = 1.0; d.naxis = 0; }
+        d.fs = a.fs; d.L1 = L1; d.N2 = N2; d.df_out = d_df; d.s_out = d_sbin; d.lrow = d_lrow; d.lcol = d_lcol;
+        d.nsplit = 8;
+        be->template launch<KDfFinal>(dim3(d.nsplit, lanes, 1), d);
+    }
+
+    int estimate(const RunArgs& a, const EstimatorCfg& e) override
+    {
+        const int lanes = a.nrec * a.nch;
+        if (lanes > max_lanes) return -2;
+        if (e.sub_mean) means(a);
+        have_means = e.sub_mean != 0;
+        col_raw(a, e.power, e.sub_mean);
+        RowParams r{};
+        r.src = d_A; r.blob = d_blob_r; r.N = N; r.N1 = L1; r.win_lo = e.win_lo; r.win_hi = e.win_hi;
+        r.part_key = d_keyrow; r.nq = 1; r.nblk = NROWBLK;
+        be->template launch<KRow<RS, RPC, ROW_FWD_ARGMAX>>(dim3(NROWBLK, lanes, 1), r);
+        df_final(a, &e);
+        return be->ok() ? 0 : -1;
+    }
+
+    // correlate windows with df taken from d_df (left there by estimate()) or from a.d_df_in
+    int correlate(const RunArgs& a) override
+    {
+        const int lanes = a.nrec * a.nch;
+        if (lanes > max_lanes) return -2;
+        if (!(a.estimate && have_means)) means(a);
+        have_means = false;
+        if (!a.estimate) df_final(a, nullptr);
+        col_raw(a, 1, 1);
+        RowParams r{};
+        r.src = d_A; r.dst = d_P; r.blob = d_blob_r; r.N = N; r.N1 = L1; r.code = d_code;
+        r.conj_mode = a.variant; r.part_energy = d_energy; r.y0 = d_y0; r.nq = 1; r.nblk = NROWBLK;
+        be->template launch<KRow<RS, RPC, ROW_FWD_MULCODE>>(dim3(NROWBLK, lanes, 1), r);
+        RowParams t{};
+        t.src = d_P; t.dst = d_B; t.blob = d_blob_r; t.N = N; t.N1 = L1; t.twq = d_twq; t.nq = nq; t.nblk = NROWBLK;
+        be->template launch<KRow<RS, RPC, ROW_INV_TWIST>>(dim3(NROWBLK, lanes, nq), t);
+        ColParams c{};
+        c.src = d_B; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.nch = 1; c.nq = nq; c.part_key = d_keycol;
+        c.ntile = NCOLTILE;
+        be->template launch<KCol<CS, TS, SRC_CF32, COL_INV_ARGMAX>>(dim3(NCOLTILE, lanes * nq, 1), c);
+        PeakTabParams pt{};
+        pt.part_key = d_keycol; pt.npart = nq * NCOLTILE; pt.N = N; pt.nq = nq; pt.L1 = L1; pt.N2 = N2;
+        pt.p0_out = d_p0; pt.rowph = d_rowph; pt.wk2 = d_wk2; pt.nsplit = 16;
+        be->template launch<KPeakTables>(dim3(pt.nsplit, lanes, 1), pt);
+        PeakSumParams ps{};
+        ps.P = d_P; ps.rowph = d_rowph; ps.wk2 = d_wk2; ps.N = N; ps.L1 = L1; ps.N2 = N2; ps.part = d_peakpart;
+        ps.nblk = NPEAKBLK;
+        be->template launch<KPeakSums<L1>>(dim3(NPEAKBLK, lanes, 1), ps);
+        PeakFinParams pf{};
+        pf.part = d_peakpart; pf.nblk = NPEAKBLK; pf.part_energy = d_energy; pf.nen = NROWBLK; pf.y0 = d_y0;
+        pf.p0 = d_p0; pf.df = d_df; pf.sbin = d_sbin; pf.N = N; pf.nq = nq; pf.variant = a.variant; pf.ddof = a.ddof;
+        pf.out = a.d_out;
+        be->template launch<KPeakFinal>(dim3(1, lanes, 1), pf);
+        return be->ok() ? 0 : -1;
+    }
+
+    // test hooks: copy an intermediate of one lane to the host
+    int debug_fetch(int what, int lane, void* host_out, size_t bytes) override
+    {
+        const void* src = nullptr;
+        switch (what) {
+        case 0: src = d_code; break;
+        case 1: src = d_A + (size_t)lane * N; break;
+        case 2: src = d_P + (size_t)lane * N; break;
+        case 3: src = d_B + (size_t)lane * nq * N; break;
+        case 4: src = d_sums + (size_t)lane * 2; break;
+        case 5: src = d_df + lane; break;
+        case 6: src = d_p0 + lane; break;
+        case 7: src = d_sbin + lane; break;
+        default: return -1;
+        }
+        be->d2h(host_out, src, bytes);
+        be->sync();
+        return be->ok() ? 0 : -1;
+    }
+};
+
+// Supported window lengths N = (column length) x (row length).
+inline IPipe* make_pipe(i64 n)
+{
+    typedef FFTSpec<20, 20, 20> R8000;
+    typedef FFTSpec<20, 20> R400;
+    switch (n) {
+    case 5000000: return new Pipe<FFTSpec<25, 25>, R8000, 1, 16>();    // 1-s window, 2.5 Mchip/s code
+    case 1000000: return new Pipe<FFTSpec<5, 25>, R8000, 1, 16>();     // 500 kchip codes
+    case 200000: return new Pipe<FFTSpec<25>, R8000, 1, 64>();         // 100 kchip/s code windows
+    case 250000: return new Pipe<FFTSpec<25, 25>, R400, 5, 16>();      // test size (same column kernel as 5e6)
+    case 10000: return new Pipe<FFTSpec<25>, R400, 5, 16>();           // 5 kchip codes / test size
+    default: return nullptr;
+    }
+}
+
+}  // namespace twstft

@@ -1,0 +1,438 @@
+// C ABI (include/twstft.h) over the kernel pipeline.  Host-side logic only: configuration,
+// window arithmetic identical to the reference's linspace/find, batching, copies.
+#include "../../include/twstft.h"
+#include "pipeline.cuh"
+#include <string>
+#include <vector>
+#include <stdio.h>
+
+using namespace twstft;
+
+static_assert(sizeof(twstft_result) == sizeof(Result), "public result row must match the device row");
+
+struct twstft_plan {
+    twstft_config cfg;
+    Backend be;
+    IPipe* pipe = nullptr;
+    EstimatorCfg est;
+    int nch = 2;
+    int nq = 3;
+    int max_lanes = 0;
+    bool have_code = false;
+    short2* d_raw = nullptr;       // staging for host inputs: max_batch records
+    size_t raw_elems_per_rec = 0;
+    Result* d_res = nullptr;
+    double* d_dfin = nullptr;
+    i64* d_off = nullptr;
+    unsigned char* d_bits = nullptr;
+    size_t bits_cap = 0;
+    std::string err;
+};
+
+static int fail(twstft_plan* p, int code, const std::string& msg)
+{
+    if (p) p->err = msg;
+    return code;
+}
+
+static double axis_value(const EstimatorCfg& e, i64 s)
+{
+    if (s == e.naxis - 1) return e.flast;
+    volatile double prod = (double)s * e.fstep;      // two roundings, like numpy/Octave linspace
+    volatile double v = prod + e.f0;
+    return v;
+}
+
+// k=find((freq<hi)&(freq>lo)) on freq=linspace(...): returns the inclusive index range
+static void window_bins(const EstimatorCfg& e, double lo, double hi, i64* slo, i64* shi)
+{
+    i64 a = (i64)floor((lo - e.f0) / e.fstep) - 3;
+    if (a < 0) a = 0;
+    while (a < e.naxis && !(axis_value(e, a) > lo)) a++;
+    i64 b = (i64)ceil((hi - e.f0) / e.fstep) + 3;
+    if (b > e.naxis - 1) b = e.naxis - 1;
+    while (b >= 0 && !(axis_value(e, b) < hi)) b--;
+    *slo = a;
+    *shi = b;
+}
+
+extern "C" {
+
+const char* twstft_backend(void) { return Backend::is_emulation ? "emu" : "cuda"; }
+
+void twstft_default_config(twstft_config* c)
+{
+    memset(c, 0, sizeof(*c));
+    c->fs = 5e6;
+    c->nsamples = 5000000;
+    c->samples_per_chip = 2;
+    c->variant = TWSTFT_VARIANT_G;
+    c->modulation = TWSTFT_BPSK;
+    c->nint = 1;
+    c->layout = TWSTFT_LAYOUT_INTERLEAVED2;
+    c->freq_axis = TWSTFT_AXIS_G;
+    c->win_lo_hz = -20000.0;
+    c->win_hi_hz = 20000.0;
+    c->est_sub_mean = 1;
+    c->ddof = 1;
+    c->max_batch = 4;
+    c->device_id = 0;
+}
+
+int twstft_plan_create(const twstft_config* cfg, twstft_plan** out)
+{
+    if (!cfg || !out) return TWSTFT_E_ARG;
+    *out = nullptr;
+    twstft_plan* p = new twstft_plan();
+    p->cfg = *cfg;
+    *out = p;   // returned even on failure so that twstft_last_error can be read; destroy it either way
+    if (cfg->nsamples <= 0 || cfg->max_batch <= 0 || cfg->fs <= 0 || cfg->samples_per_chip <= 0)
+        return fail(p, TWSTFT_E_ARG, "bad configuration");
+    if (cfg->nint != 0 && cfg->nint != 1)
+        return fail(p, TWSTFT_E_ARG, "only Nint=1 (x3) and Nint=0 are supported (the reference uses Nint=1)");
+    if (p->be.init(cfg->device_id) != 0)
+        return fail(p, TWSTFT_E_NODEVICE, std::string("no usable CUDA device: ") + p->be.err_string() +
+                                              " (this library has no CPU fallback)");
+    p->pipe = make_pipe(cfg->nsamples);
+    if (!p->pipe) return fail(p, TWSTFT_E_SIZE, "unsupported window length (see make_pipe in pipeline.cuh)");
+    p->nch = cfg->layout == TWSTFT_LAYOUT_INTERLEAVED2 ? 2 : 1;
+    p->nq = cfg->nint ? 3 : 1;
+    p->max_lanes = cfg->max_batch * p->nch;
+    if (p->pipe->setup(&p->be, p->max_lanes, p->nq) != 0)
+        return fail(p, TWSTFT_E_NOMEM, std::string("device allocation failed: ") + p->be.err_string());
+    const i64 N = cfg->nsamples;
+    p->raw_elems_per_rec = (size_t)N * p->nch;
+    p->d_res = (Result*)p->be.alloc(sizeof(Result) * p->max_lanes);
+    p->d_dfin = (double*)p->be.alloc(sizeof(double) * p->max_lanes);
+    p->d_off = (i64*)p->be.alloc(sizeof(i64) * cfg->max_batch);
+    // frequency axis of the estimator: length = window length
+    EstimatorCfg& e = p->est;
+    e.naxis = N;
+    e.f0 = -cfg->fs / 2;
+    e.flast = cfg->freq_axis == TWSTFT_AXIS_G ? cfg->fs / 2 : cfg->fs / 2 - 1.0;
+    e.fstep = (e.flast - e.f0) / (double)(N - 1);
+    e.power = cfg->modulation == TWSTFT_QPSK ? 4 : 2;
+    e.sub_mean = cfg->est_sub_mean;
+    window_bins(e, cfg->win_lo_hz, cfg->win_hi_hz, &e.win_lo, &e.win_hi);
+    if (e.win_lo > e.win_hi) return fail(p, TWSTFT_E_ARG, "empty estimator window");
+    if (!p->be.ok()) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
+    return TWSTFT_OK;
+}
+
+void twstft_plan_destroy(twstft_plan* p)
+{
+    if (!p) return;
+    p->be.use();
+    delete p->pipe;
+    p->be.free(p->d_raw);
+    p->be.free(p->d_res);
+    p->be.free(p->d_dfin);
+    p->be.free(p->d_off);
+    p->be.free(p->d_bits);
+    p->be.shutdown();
+    delete p;
+}
+
+const char* twstft_last_error(const twstft_plan* p) { return p ? p->err.c_str() : "null plan"; }
+
+int64_t twstft_kernel_launches(const twstft_plan* p) { return p ? p->be.launches : 0; }
+
+int twstft_window_bins(const twstft_plan* p, int64_t* lo, int64_t* hi)
+{
+    if (!p) return TWSTFT_E_ARG;
+    if (lo) *lo = p->est.win_lo;
+    if (hi) *hi = p->est.win_hi;
+    return TWSTFT_OK;
+}
+
+static int ensure_bits(twstft_plan* p, size_t n)
+{
+    if (p->bits_cap >= n) return 0;
+    p->be.free(p->d_bits);
+    p->d_bits = (unsigned char*)p->be.alloc(n);
+    p->bits_cap = n;
+    return p->be.ok() ? 0 : -1;
+}
+
+static int install_code(twstft_plan* p, const unsigned char* host_bits, size_t nbytes, int qpsk)
+{
+    const size_t nchips = qpsk ? nbytes / 2 : nbytes;
+    if ((i64)nchips * p->cfg.samples_per_chip != p->cfg.nsamples)
+        return fail(p, TWSTFT_E_ARG, "code length * samples_per_chip != nsamples");
+    float2 mean = make_float2(0.f, 0.f);
+    if (qpsk) {   // goqpsk.m:11-12 codec=codei+j*codeq; codec=codec-mean(codec)
+        double sa = 0, sb = 0;
+        for (size_t i = 0; i < nchips; i++) { sa += host_bits[2 * i]; sb += host_bits[2 * i + 1]; }
+        mean = make_float2((float)(sa / (double)nchips), (float)(sb / (double)nchips));
+    }
+    if (p->pipe->build_code(p->d_bits, p->cfg.samples_per_chip, qpsk, mean) != 0)
+        return fail(p, TWSTFT_E_CUDA, p->be.err_string());
+    p->be.sync();
+    if (!p->be.ok()) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
+    p->have_code = true;
+    return TWSTFT_OK;
+}
+
+int twstft_set_code(twstft_plan* p, const uint8_t* chips, size_t nbytes, int qpsk)
+{
+    if (!p || !chips || !p->pipe) return TWSTFT_E_ARG;
+    p->be.use();
+    if (ensure_bits(p, nbytes) != 0) return fail(p, TWSTFT_E_NOMEM, "device allocation failed");
+    p->be.h2d(p->d_bits, chips, nbytes);
+    p->be.sync();
+    return install_code(p, chips, nbytes, qpsk);
+}
+
+// GF(2) jump matrices of the LFSR step: column i of M^(2^j)
+static void lfsr_jump_tables(int bitlen, unsigned taps, unsigned jump[24][24])
+{
+    auto step = [&](unsigned s) {
+        unsigned x = s & taps;
+        x ^= x >> 16; x ^= x >> 8; x ^= x >> 4; x ^= x >> 2; x ^= x >> 1;
+        return (s >> 1) | ((x & 1u) << (bitlen - 1));
+    };
+    memset(jump, 0, sizeof(unsigned) * 24 * 24);
+    for (int i = 0; i < bitlen; i++) jump[0][i] = step(1u << i);
+    for (int j = 1; j < 24; j++)
+        for (int i = 0; i < bitlen; i++) {
+            unsigned v = jump[j - 1][i], r = 0;
+            for (int b = 0; b < bitlen; b++)
+                if ((v >> b) & 1) r ^= jump[j - 1][b];
+            jump[j][i] = r;
+        }
+}
+
+static int prn_on_device(Backend& be, unsigned char* d_out, int bitlen, unsigned taps, unsigned seed,
+                         size_t noiselen, int ostride, int ooffset)
+{
+    PrnParams pp;
+    lfsr_jump_tables(bitlen, taps, pp.jump);
+    pp.bitlen = bitlen; pp.taps = taps; pp.seed = seed; pp.nchips = (i64)noiselen; pp.out = d_out;
+    pp.ostride = ostride; pp.ooffset = ooffset;
+    const i64 nthreads = ((i64)noiselen + KPrnGen::CH - 1) / KPrnGen::CH;
+    const int nblk = (int)((nthreads + KPrnGen::NT - 1) / KPrnGen::NT);
+    be.launch<KPrnGen>(dim3(nblk, 1, 1), pp);
+    return be.ok() ? 0 : -1;
+}
+
+int twstft_gen_code(twstft_plan* p, int bitlen, uint32_t taps_a, uint32_t taps_b, uint32_t seed,
+                    size_t noiselen, uint8_t* chips_out)
+{
+    if (!p || !p->pipe || bitlen < 2 || bitlen > 24 || noiselen == 0 || noiselen >= (1u << 24))
+        return fail(p, TWSTFT_E_ARG, "bad LFSR parameters");
+    p->be.use();
+    const int qpsk = taps_b != 0;
+    const size_t nbytes = noiselen * (qpsk ? 2 : 1);
+    if (ensure_bits(p, nbytes) != 0) return fail(p, TWSTFT_E_NOMEM, "device allocation failed");
+    prn_on_device(p->be, p->d_bits, bitlen, taps_a, seed, noiselen, qpsk ? 2 : 1, 0);
+    if (qpsk) prn_on_device(p->be, p->d_bits, bitlen, taps_b, seed, noiselen, 2, 1);
+    std::vector<unsigned char> host(nbytes);
+    p->be.d2h(host.data(), p->d_bits, nbytes);
+    p->be.sync();
+    if (!p->be.ok()) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
+    if (chips_out) memcpy(chips_out, host.data(), nbytes);
+    return install_code(p, host.data(), nbytes, qpsk);
+}
+
+int twstft_prn_generate(int device_id, int bitlen, uint32_t taps_a, uint32_t taps_b, uint32_t seed,
+                        size_t noiselen, uint8_t* out)
+{
+    if (!out || bitlen < 2 || bitlen > 24 || noiselen == 0 || noiselen >= (1u << 24)) return TWSTFT_E_ARG;
+    Backend be;
+    if (be.init(device_id) != 0) return TWSTFT_E_NODEVICE;
+    const int qpsk = taps_b != 0;
+    const size_t nbytes = noiselen * (qpsk ? 2 : 1);
+    unsigned char* d = (unsigned char*)be.alloc(nbytes);
+    prn_on_device(be, d, bitlen, taps_a, seed, noiselen, qpsk ? 2 : 1, 0);
+    if (qpsk) prn_on_device(be, d, bitlen, taps_b, seed, noiselen, 2, 1);
+    be.d2h(out, d, nbytes);
+    be.sync();
+    be.free(d);
+    const bool ok = be.ok();
+    be.shutdown();
+    return ok ? TWSTFT_OK : TWSTFT_E_CUDA;
+}
+
+static int ensure_raw(twstft_plan* p)
+{
+    if (p->d_raw) return 0;
+    p->d_raw = (short2*)p->be.alloc(sizeof(short2) * p->raw_elems_per_rec * p->cfg.max_batch);
+    return p->be.ok() ? 0 : -1;
+}
+
+// records resident on the device, contiguous
+static int process_dev(twstft_plan* p, const short2* d_iq, size_t nrecords, twstft_result* results)
+{
+    const int B = p->cfg.max_batch;
+    for (size_t r0 = 0; r0 < nrecords; r0 += B) {
+        const int nb = (int)((nrecords - r0) < (size_t)B ? (nrecords - r0) : B);
+        RunArgs a{};
+        a.d_raw = d_iq + r0 * p->raw_elems_per_rec;
+        a.nrec = nb; a.nch = p->nch; a.rec_stride = (i64)p->raw_elems_per_rec; a.d_rec_offset = nullptr;
+        a.estimate = 1; a.variant = p->cfg.variant; a.ddof = p->cfg.ddof; a.fs = p->cfg.fs; a.d_out = p->d_res;
+        if (p->pipe->estimate(a, p->est) != 0 || p->pipe->correlate(a) != 0)
+            return fail(p, TWSTFT_E_CUDA, p->be.err_string());
+        p->be.d2h(results + r0 * p->nch, p->d_res, sizeof(Result) * nb * p->nch);
+        p->be.sync();
+        if (!p->be.ok()) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
+    }
+    return TWSTFT_OK;
+}
+
+int twstft_process_device(twstft_plan* p, const int16_t* iq_dev, size_t nrecords, twstft_result* results)
+{
+    if (!p || !p->pipe || !iq_dev || !results) return TWSTFT_E_ARG;
+    if (!p->have_code) return fail(p, TWSTFT_E_NOCODE, "no PRN code installed (twstft_set_code / twstft_gen_code)");
+    p->be.use();
+    return process_dev(p, reinterpret_cast<const short2*>(iq_dev), nrecords, results);
+}
+
+int twstft_process(twstft_plan* p, const int16_t* iq, size_t nrecords, twstft_result* results)
+{
+    if (!p || !p->pipe || !iq || !results) return TWSTFT_E_ARG;
+    if (!p->have_code) return fail(p, TWSTFT_E_NOCODE, "no PRN code installed (twstft_set_code / twstft_gen_code)");
+    p->be.use();
+    if (ensure_raw(p) != 0) return fail(p, TWSTFT_E_NOMEM, "device allocation failed");
+    const int B = p->cfg.max_batch;
+    const short2* h = reinterpret_cast<const short2*>(iq);
+    for (size_t r0 = 0; r0 < nrecords; r0 += B) {
+        const size_t nb = (nrecords - r0) < (size_t)B ? (nrecords - r0) : B;
+        p->be.h2d(p->d_raw, h + r0 * p->raw_elems_per_rec, sizeof(short2) * p->raw_elems_per_rec * nb);
+        int rc = process_dev(p, p->d_raw, nb, results + r0 * p->nch);
+        if (rc != 0) return rc;
+    }
+    return TWSTFT_OK;
+}
+
+int twstft_process_windows(twstft_plan* p, const int16_t* iq, int on_device, size_t total_instants,
+                           const int64_t* offsets, const double* df, size_t nwin, twstft_result* results)
+{
+    if (!p || !p->pipe || !iq || !offsets || !df || !results) return TWSTFT_E_ARG;
+    if (!p->have_code) return fail(p, TWSTFT_E_NOCODE, "no PRN code installed");
+    p->be.use();
+    const i64 N = p->cfg.nsamples;
+    for (size_t i = 0; i < nwin; i++)
+        if (offsets[i] < 0 || (size_t)(offsets[i] + N) > total_instants)
+            return fail(p, TWSTFT_E_ARG, "window outside the buffer");
+    const short2* d_iq = reinterpret_cast<const short2*>(iq);
+    short2* tmp = nullptr;
+    if (!on_device) {
+        tmp = (short2*)p->be.alloc(sizeof(short2) * total_instants * p->nch);
+        if (!p->be.ok()) return fail(p, TWSTFT_E_NOMEM, "device allocation failed");
+        p->be.h2d(tmp, iq, sizeof(short2) * total_instants * p->nch);
+        d_iq = tmp;
+    }
+    const int B = p->cfg.max_batch;
+    int rc = TWSTFT_OK;
+    std::vector<i64> off(B);
+    for (size_t w0 = 0; w0 < nwin && rc == TWSTFT_OK; w0 += B) {
+        const int nb = (int)((nwin - w0) < (size_t)B ? (nwin - w0) : B);
+        for (int i = 0; i < nb; i++) off[i] = offsets[w0 + i] * p->nch;
+        p->be.h2d(p->d_off, off.data(), sizeof(i64) * nb);
+        p->be.h2d(p->d_dfin, df + w0 * p->nch, sizeof(double) * nb * p->nch);
+        RunArgs a{};
+        a.d_raw = d_iq; a.nrec = nb; a.nch = p->nch; a.rec_stride = 0; a.d_rec_offset = p->d_off;
+        a.estimate = 0; a.d_df_in = p->d_dfin; a.variant = p->cfg.variant; a.ddof = p->cfg.ddof;
+        a.fs = p->cfg.fs; a.d_out = p->d_res;
+        if (p->pipe->correlate(a) != 0) { rc = fail(p, TWSTFT_E_CUDA, p->be.err_string()); break; }
+        p->be.d2h(results + w0 * p->nch, p->d_res, sizeof(Result) * nb * p->nch);
+        p->be.sync();
+        if (!p->be.ok()) rc = fail(p, TWSTFT_E_CUDA, p->be.err_string());
+    }
+    if (tmp) { p->be.sync(); p->be.free(tmp); }
+    return rc;
+}
+
+int twstft_estimate_carrier(twstft_plan* p, const int16_t* iq, int on_device, size_t nrecords,
+                            double* df, int64_t* bins)
+{
+    if (!p || !p->pipe || !iq) return TWSTFT_E_ARG;
+    p->be.use();
+    if (!on_device && ensure_raw(p) != 0) return fail(p, TWSTFT_E_NOMEM, "device allocation failed");
+    const int B = p->cfg.max_batch;
+    const short2* src = reinterpret_cast<const short2*>(iq);
+    for (size_t r0 = 0; r0 < nrecords; r0 += B) {
+        const int nb = (int)((nrecords - r0) < (size_t)B ? (nrecords - r0) : B);
+        const short2* d = src + r0 * p->raw_elems_per_rec;
+        if (!on_device) {
+            p->be.h2d(p->d_raw, d, sizeof(short2) * p->raw_elems_per_rec * nb);
+            d = p->d_raw;
+        }
+        RunArgs a{};
+        a.d_raw = d; a.nrec = nb; a.nch = p->nch; a.rec_stride = (i64)p->raw_elems_per_rec;
+        a.estimate = 1; a.variant = p->cfg.variant; a.ddof = p->cfg.ddof; a.fs = p->cfg.fs; a.d_out = p->d_res;
+        if (p->pipe->estimate(a, p->est) != 0) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
+        for (int l = 0; l < nb * p->nch; l++) {
+            if (df) p->pipe->debug_fetch(5, l, df + r0 * p->nch + l, sizeof(double));
+            if (bins) p->pipe->debug_fetch(7, l, bins + r0 * p->nch + l, sizeof(i64));
+        }
+        p->be.sync();
+        if (!p->be.ok()) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
+    }
+    return TWSTFT_OK;
+}
+
+void* twstft_host_alloc(size_t bytes)
+{
+#ifdef TWSTFT_EMU
+    return malloc(bytes);
+#else
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+#endif
+}
+void twstft_host_free(void* p)
+{
+#ifdef TWSTFT_EMU
+    free(p);
+#else
+    if (p) cudaFreeHost(p);
+#endif
+}
+int twstft_device_alloc(twstft_plan* p, size_t bytes, void** out)
+{
+    if (!p || !out) return TWSTFT_E_ARG;
+    p->be.use();
+    *out = p->be.alloc(bytes);
+    return (*out && p->be.ok()) ? TWSTFT_OK : fail(p, TWSTFT_E_NOMEM, "device allocation failed");
+}
+int twstft_device_free(twstft_plan* p, void* d)
+{
+    if (!p) return TWSTFT_E_ARG;
+    p->be.use();
+    p->be.sync();
+    p->be.free(d);
+    return TWSTFT_OK;
+}
+int twstft_copy_to_device(twstft_plan* p, void* dst, const void* src, size_t bytes)
+{
+    if (!p) return TWSTFT_E_ARG;
+    p->be.use();
+    p->be.h2d(dst, src, bytes);
+    p->be.sync();
+    return p->be.ok() ? TWSTFT_OK : fail(p, TWSTFT_E_CUDA, p->be.err_string());
+}
+int twstft_copy_to_host(twstft_plan* p, void* dst, const void* src, size_t bytes)
+{
+    if (!p) return TWSTFT_E_ARG;
+    p->be.use();
+    p->be.d2h(dst, src, bytes);
+    p->be.sync();
+    return p->be.ok() ? TWSTFT_OK : fail(p, TWSTFT_E_CUDA, p->be.err_string());
+}
+int twstft_synchronize(twstft_plan* p)
+{
+    if (!p) return TWSTFT_E_ARG;
+    p->be.use();
+    p->be.sync();
+    return p->be.ok() ? TWSTFT_OK : fail(p, TWSTFT_E_CUDA, p->be.err_string());
+}
+int twstft_debug_fetch(twstft_plan* p, int what, int lane, void* host_out, size_t bytes)
+{
+    if (!p || !p->pipe) return TWSTFT_E_ARG;
+    p->be.use();
+    return p->pipe->debug_fetch(what, lane, host_out, bytes);
+}
+
+}  // extern "C"

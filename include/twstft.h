@@ -1,0 +1,136 @@
+/*
+ * twstft.h -- C ABI of the B200-native amaranth_twstft post-processing correlator.
+ *
+ * The reference has no FFI; this ABI is drawn at its narrowest seams.
+ * Each entry point names the reference interface it replaces (paths relative to the reference root):
+ *
+ *   twstft_plan_create   script set-up: fs/Nint/windows/code spectrum
+ *                        processing/Octave/godual_ranging.m:3-10,62-73
+ *                        acquisition/claudio_aligned_code_lo_separate.m:7-22,92-113
+ *                        processing/CPP/main.cpp:93-189 (GoRanging ctor)
+ *   twstft_set_code      code=fread(f,inf,'int8') ... fcode=conj(fft(code'))      godual_ranging.m:62-66
+ *   twstft_gen_code      write_prn_seq / nextstate                                amaranth_twstft/common.py:23-30,59-73
+ *   twstft_process       the record loop + processing(d,k) of variant G           godual_ranging.m:12-49,75-102
+ *                        (= GoRanging::compute + _process_method,                 processing/CPP/main.cpp:224-361,452-519)
+ *   twstft_process_windows  processing(d,k,df) / processing(d,df) of variant K   claudio_aligned_code_lo_separate.m:24-77
+ *                                                                                 claudio_aligned_code_re_separate.m:48-101
+ *   twstft_estimate_carrier  d2=fftshift(abs(fft(d.^2))); [~,df]=max(d2(k))      godual_ranging.m:14-15, lo_separate.m:126-129
+ *   twstft_result        one row of the .mat variables                            godual_ranging.m:128-130, lo_separate.m:166
+ *
+ * Conventions: plain C, caller owns every host buffer, the plan owns device memory and streams,
+ * int return codes (0 = ok, <0 = error, text via twstft_last_error), never an exception or a
+ * torch type across the ABI.  One plan per GPU; a plan is not re-entrant; different plans may be
+ * driven from different host threads.  There is NO CPU fallback: plan creation fails without a
+ * CUDA device.
+ */
+#ifndef TWSTFT_H
+#define TWSTFT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TWSTFT_VARIANT_G 0 /* godual_ranging.m: fcode=conj(fft(code)), P=ffty.*fcode           */
+#define TWSTFT_VARIANT_K 1 /* claudio_aligned_code_*: fcode=fft(code), P=fcode.*conj(ffty)     */
+
+#define TWSTFT_BPSK 0 /* carrier from fft(x.^2), df=freq/2 */
+#define TWSTFT_QPSK 1 /* carrier from fft(x.^4), df=freq/4 (Doc/07_Demodulation.md:60-63) */
+
+#define TWSTFT_LAYOUT_INTERLEAVED2 0 /* [I1 Q1 I2 Q2] int16 per sample instant (b210_file.py:60-65)   */
+#define TWSTFT_LAYOUT_SINGLE 1       /* [I Q] int16, one channel per file (rx_multi_samples.cpp:214)  */
+
+#define TWSTFT_AXIS_G 0 /* freq=linspace(-fs/2,fs/2,n)      godual_ranging.m:73   */
+#define TWSTFT_AXIS_K 1 /* freq=linspace(-fs/2,fs/2-1,n)    lo_separate.m:103     */
+
+#define TWSTFT_OK 0
+#define TWSTFT_E_ARG (-1)
+#define TWSTFT_E_NODEVICE (-2)
+#define TWSTFT_E_SIZE (-3)   /* unsupported window length */
+#define TWSTFT_E_CUDA (-4)
+#define TWSTFT_E_NOCODE (-5)
+#define TWSTFT_E_NOMEM (-6)
+
+typedef struct twstft_plan twstft_plan;
+
+typedef struct twstft_config {
+    double fs;          /* sample rate, 5e6 */
+    int64_t nsamples;   /* N: samples per correlation window = samples_per_chip * code length */
+    int samples_per_chip; /* fs/fchip, 2 */
+    int variant;        /* TWSTFT_VARIANT_* */
+    int modulation;     /* TWSTFT_BPSK / TWSTFT_QPSK */
+    int nint;           /* Nint: 1 -> x3 interpolation (the only value the reference uses), 0 -> none */
+    int layout;         /* TWSTFT_LAYOUT_* */
+    int freq_axis;      /* TWSTFT_AXIS_* */
+    double win_lo_hz;   /* estimator window k=find((freq<hi)&(freq>lo)), strict */
+    double win_hi_hz;
+    int est_sub_mean;   /* 1: estimator squares the mean-removed window (G), 0: raw (K) */
+    int ddof;           /* 1: Octave var (n-1), 0: numpy/C++ var (n) */
+    int max_batch;      /* records (or windows) per device batch */
+    int device_id;
+} twstft_config;
+
+/* One row of the reference's result variables, per channel and record (all doubles). */
+typedef struct twstft_result {
+    double indice;        /* 1-based index of the maximum on the interpolated grid */
+    double correction;    /* parabolic vertex offset in interpolated samples */
+    double xval_re, xval_im;
+    double xvalm1_re, xvalm1_im;
+    double xvalp1_re, xvalp1_im;
+    double SNRr, SNRi;
+    double df;            /* carrier offset used for the derotation, Hz */
+    double puissance, puissancecode, puissancenoise;
+    double carrier_bin;   /* 0-based index of the estimator maximum on the fftshift'ed axis, -1 if df was given */
+    double status;        /* bit0: peak at the array edge (Octave would fail), bit1: fp64 refinement moved the peak */
+} twstft_result;
+
+void twstft_default_config(twstft_config* cfg);
+int twstft_plan_create(const twstft_config* cfg, twstft_plan** out);
+void twstft_plan_destroy(twstft_plan* plan);
+const char* twstft_last_error(const twstft_plan* plan);
+const char* twstft_backend(void); /* "cuda" for the product library */
+
+/* PRN replica. chips: 0/1 bytes; qpsk!=0 -> generator A and B bytes interleaved (common.py:66-71). */
+int twstft_set_code(twstft_plan* plan, const uint8_t* chips, size_t nbytes, int qpsk);
+/* Generate the LFSR code(s) on the GPU, install the replica, optionally return the chip bytes. */
+int twstft_gen_code(twstft_plan* plan, int bitlen, uint32_t taps_a, uint32_t taps_b, uint32_t seed,
+                    size_t noiselen, uint8_t* chips_out);
+/* Stand-alone GPU LFSR (no plan state): out[noiselen] (taps_b==0) or out[2*noiselen] interleaved. */
+int twstft_prn_generate(int device_id, int bitlen, uint32_t taps_a, uint32_t taps_b, uint32_t seed,
+                        size_t noiselen, uint8_t* out);
+
+/* Variant-G record loop: nrecords consecutive records of nch*N complex-int16 samples in HOST memory;
+ * results[record*nch + ch].  Estimates the carrier per record and channel, then correlates. */
+int twstft_process(twstft_plan* plan, const int16_t* iq, size_t nrecords, twstft_result* results);
+/* Same with the records already resident in DEVICE memory. */
+int twstft_process_device(twstft_plan* plan, const int16_t* iq_dev, size_t nrecords, twstft_result* results);
+
+/* Variant-K style: nwin windows of N samples starting at sample instants offsets[i] of a (host or
+ * device) buffer holding `total_instants` sample instants, derotated by the given df[i*nch+ch]. */
+int twstft_process_windows(twstft_plan* plan, const int16_t* iq, int iq_on_device, size_t total_instants,
+                           const int64_t* offsets, const double* df, size_t nwin, twstft_result* results);
+
+/* Carrier estimator alone (A3): df[record*nch+ch], bins[...] = 0-based index on the shifted axis. */
+int twstft_estimate_carrier(twstft_plan* plan, const int16_t* iq, int iq_on_device, size_t nrecords,
+                            double* df, int64_t* bins);
+
+/* Pinned host memory for the end-to-end path, device memory helpers for device-resident inputs. */
+void* twstft_host_alloc(size_t bytes);
+void twstft_host_free(void* p);
+int twstft_device_alloc(twstft_plan* plan, size_t bytes, void** out);
+int twstft_device_free(twstft_plan* plan, void* p);
+int twstft_copy_to_device(twstft_plan* plan, void* dst_dev, const void* src_host, size_t bytes);
+int twstft_copy_to_host(twstft_plan* plan, void* dst_host, const void* src_dev, size_t bytes);
+int twstft_synchronize(twstft_plan* plan);
+
+/* Introspection used by tests and the benchmark. */
+int64_t twstft_kernel_launches(const twstft_plan* plan);   /* kernels launched so far by this plan */
+int twstft_debug_fetch(twstft_plan* plan, int what, int lane, void* host_out, size_t bytes);
+int twstft_window_bins(const twstft_plan* plan, int64_t* lo, int64_t* hi);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TWSTFT_H */

@@ -1,0 +1,65 @@
+// TEST INFRASTRUCTURE ONLY (never compiled into the product library).
+// Host emulation backend: runs the __host__ __device__ kernel phases of amaranth_twstft_b200/csrc
+// thread by thread, with barriers/reductions between phases performed by this driver, so that the
+// CPU test-suite can validate the CUDA kernels' index arithmetic without a GPU.
+#pragma once
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+namespace twstft {
+
+template <class K, int PH> struct EmuPhases {
+    static void run(const typename K::Params& p, const Blk& b, std::vector<typename K::Regs>& regs, unsigned char* smem)
+    {
+        for (int tid = 0; tid < K::NT; tid++) K::template phase<PH>(p, b, tid, regs[tid], smem);
+        if constexpr (PH + 1 < K::NPH) {
+            constexpr int kind = K::sync_after(PH);
+            if constexpr (kind == SYNC_MAXKEY || kind == SYNC_MAXKEY_SUMD) {
+                u64 best = 0;
+                for (int tid = 0; tid < K::NT; tid++) best = regs[tid].key > best ? regs[tid].key : best;
+                for (int tid = 0; tid < K::NT; tid++) regs[tid].key = best;
+            }
+            if constexpr (kind == SYNC_SUMD || kind == SYNC_MAXKEY_SUMD) {
+                for (int i = 0; i < K::NSUM; i++) {
+                    double t = 0.0;
+                    for (int tid = 0; tid < K::NT; tid++) t += regs[tid].dsum[i];
+                    regs[0].dsum[i] = t;
+                }
+            }
+            EmuPhases<K, PH + 1>::run(p, b, regs, smem);
+        }
+    }
+};
+
+struct Backend {
+    static constexpr bool is_emulation = true;
+    int device = 0;
+    int err = 0;
+    long launches = 0;
+    bool ok() const { return err == 0; }
+    const char* err_string() const { return "emulation backend error"; }
+    int init(int) { return 0; }
+    void shutdown() {}
+    void use() {}
+    void* alloc(size_t bytes) { return calloc(bytes ? bytes : 1, 1); }
+    void free(void* p) { ::free(p); }
+    void zero(void* p, size_t bytes) { memset(p, 0, bytes); }
+    void h2d(void* d, const void* h, size_t bytes) { memcpy(d, h, bytes); }
+    void d2h(void* h, const void* d, size_t bytes) { memcpy(h, d, bytes); }
+    void sync() {}
+    template <class K> void launch(dim3 grid, const typename K::Params& p)
+    {
+        std::vector<unsigned char> smem(K::smem_bytes() + 64);
+        std::vector<typename K::Regs> regs(K::NT);
+        for (unsigned z = 0; z < grid.z; z++)
+            for (unsigned y = 0; y < grid.y; y++)
+                for (unsigned x = 0; x < grid.x; x++) {
+                    Blk b{(int)x, (int)y, (int)z};
+                    EmuPhases<K, 0>::run(p, b, regs, smem.data());
+                }
+        launches++;
+    }
+};
+
+}  // namespace twstft
