@@ -22,7 +22,7 @@ EXPORTS = [
     "twstft_process_device", "twstft_process_windows", "twstft_estimate_carrier", "twstft_host_alloc",
     "twstft_host_free", "twstft_device_alloc", "twstft_device_free", "twstft_copy_to_device",
     "twstft_copy_to_host", "twstft_synchronize", "twstft_kernel_launches", "twstft_debug_fetch",
-    "twstft_window_bins",
+    "twstft_window_bins", "twstft_timer_start", "twstft_timer_stop", "twstft_profile_enable", "twstft_profile_read",
 ]
 
 
@@ -90,5 +90,9 @@ def load(path=None):
     lib.twstft_kernel_launches.restype = C.c_int64
     lib.twstft_debug_fetch.argtypes = [P, C.c_int, C.c_int, P, C.c_size_t]
     lib.twstft_window_bins.argtypes = [P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.twstft_timer_start.argtypes = [P]
+    lib.twstft_timer_stop.argtypes = [P, C.POINTER(C.c_float)]
+    lib.twstft_profile_enable.argtypes = [P, C.c_int]
+    lib.twstft_profile_read.argtypes = [P, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     _cache[path] = lib
     return lib

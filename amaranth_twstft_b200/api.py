@@ -57,6 +57,9 @@ class Correlator:
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
+        for ptr in getattr(self, "_pinned", []):
+            self.lib.twstft_host_free(ptr)
+        self._pinned = []
         if getattr(self, "_plan", None):
             self.lib.twstft_plan_destroy(self._plan)
             self._plan = C.c_void_p()
@@ -146,6 +149,38 @@ class Correlator:
         self._check(self.lib.twstft_estimate_carrier(self._plan, iq.ctypes.data, 0, nrec, df.ctypes.data,
                                                      bins.ctypes.data), "twstft_estimate_carrier")
         return df, bins
+
+    # ------------------------------------------------------------------ timing (CUDA events on the plan's stream)
+    def timer_start(self):
+        self._check(self.lib.twstft_timer_start(self._plan), "twstft_timer_start")
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._check(self.lib.twstft_timer_stop(self._plan, C.byref(ms)), "twstft_timer_stop")
+        return float(ms.value)
+
+    def profile(self, on):
+        self.lib.twstft_profile_enable(self._plan, int(on))
+
+    def profile_read(self):
+        """{kernel name: (total ms, launches)} accumulated while profiling was enabled."""
+        out, slot = {}, 0
+        name = C.create_string_buffer(64)
+        ms, cnt = C.c_double(), C.c_int64()
+        while self.lib.twstft_profile_read(self._plan, slot, name, 64, C.byref(ms), C.byref(cnt)) == 0:
+            out[name.value.decode()] = (ms.value, cnt.value)
+            slot += 1
+        return out
+
+    def pinned_empty(self, nbytes):
+        """uint8 numpy view over pinned host memory (twstft_host_alloc); keep the Correlator alive."""
+        ptr = self.lib.twstft_host_alloc(nbytes)
+        if not ptr:
+            raise TwstftError("twstft_host_alloc failed")
+        buf = (C.c_uint8 * nbytes).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=np.uint8)
+        self._pinned = getattr(self, "_pinned", []) + [ptr]
+        return arr
 
     # ------------------------------------------------------------------ device memory helpers
     def to_device(self, arr):

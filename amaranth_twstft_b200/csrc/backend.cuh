@@ -14,6 +14,7 @@
 #else
 #include <stdio.h>
 #include <string.h>
+#include <vector>
 
 namespace twstft {
 
@@ -60,10 +61,60 @@ struct Backend {
     void h2d(void* d, const void* h, size_t bytes) { note(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream)); }
     void d2h(void* h, const void* d, size_t bytes) { note(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, stream)); }
     void sync() { note(cudaStreamSynchronize(stream)); }
+    // optional per-kernel CUDA-event profiling (bench.py roofline leg): one event pair per launch
+    struct ProfSlot { const char* name; double ms; long count; };
+    bool profiling = false;
+    std::vector<ProfSlot> prof;
+    struct Pending { int slot; cudaEvent_t a, b; };
+    std::vector<Pending> pending;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+
+    int prof_slot(const char* name)
+    {
+        for (size_t i = 0; i < prof.size(); i++)
+            if (!strcmp(prof[i].name, name)) return (int)i;
+        prof.push_back(ProfSlot{name, 0.0, 0});
+        return (int)prof.size() - 1;
+    }
+    void prof_collect()
+    {
+        sync();
+        for (auto& pe : pending) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, pe.a, pe.b) == cudaSuccess) { prof[pe.slot].ms += ms; prof[pe.slot].count++; }
+            cudaEventDestroy(pe.a);
+            cudaEventDestroy(pe.b);
+        }
+        pending.clear();
+    }
+    void timer_start()
+    {
+        if (!t0) { cudaEventCreate(&t0); cudaEventCreate(&t1); }
+        note(cudaEventRecord(t0, stream));
+    }
+    float timer_stop()
+    {
+        float ms = -1.f;
+        note(cudaEventRecord(t1, stream));
+        note(cudaEventSynchronize(t1));
+        note(cudaEventElapsedTime(&ms, t0, t1));
+        return ms;
+    }
     template <class K> void launch(dim3 grid, const typename K::Params& p)
     {
         DeviceLauncher l{stream};
-        l.launch<K>(grid, p);
+        if (profiling) {
+            Pending pe;
+            pe.slot = prof_slot(K::name());
+            cudaEventCreate(&pe.a);
+            cudaEventCreate(&pe.b);
+            cudaEventRecord(pe.a, stream);
+            l.launch<K>(grid, p);
+            cudaEventRecord(pe.b, stream);
+            pending.push_back(pe);
+        } else {
+            l.launch<K>(grid, p);
+        }
         note(l.err);
         launches++;
     }

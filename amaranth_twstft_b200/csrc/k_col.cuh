@@ -44,6 +44,11 @@ struct ColParams {
 
 template <class S, int TS, int SRC, int MODE> struct KCol {
     typedef ColParams Params;
+    static const char* name()
+    {
+        return MODE == COL_INV_ARGMAX ? "col_inv_argmax" : MODE == COL_INV_STORE ? "col_inv_store"
+             : SRC == SRC_RAW ? "col_fwd_raw" : SRC == SRC_BITS ? "col_fwd_bits" : "col_fwd_cf32";
+    }
     static constexpr int NTA = S::NTS * TS;
     static constexpr int NT = (NTA + 31) / 32 * 32;
     static constexpr int MINB = (S::L * TS >= 8000) ? 2 : 4;

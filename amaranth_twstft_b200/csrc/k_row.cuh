@@ -42,6 +42,11 @@ struct RowParams {
 
 template <class S, int RPC, int MODE> struct KRow {
     typedef RowParams Params;
+    static const char* name()
+    {
+        return MODE == ROW_FWD_STORE ? "row_fwd_store" : MODE == ROW_FWD_ARGMAX ? "row_fwd_argmax"
+             : MODE == ROW_FWD_MULCODE ? "row_fwd_mulcode" : "row_inv_twist";
+    }
     static constexpr int NTA = S::NTS * RPC;
     static constexpr int NT = (NTA + 31) / 32 * 32;
     static constexpr int MINB = (S::L * RPC >= 8000) ? 2 : 4;

@@ -48,6 +48,7 @@ struct MeanParams {
 };
 struct KMean {
     typedef MeanParams Params;
+    static const char* name() { return "mean"; }
     static constexpr int NT = 256, MINB = 4, NPH = 2, NSUM = 4;
     struct Regs { u64 key; double dsum[NSUM]; };
     static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }
@@ -105,6 +106,7 @@ struct DfParams {
 };
 struct KDfFinal {
     typedef DfParams Params;
+    static const char* name() { return "df_final"; }
     static constexpr int NT = 256, MINB = 4, NPH = 2, NSUM = 1;
     struct Regs { u64 key; double dsum[NSUM]; };
     static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }
@@ -165,6 +167,7 @@ struct PeakTabParams {
 };
 struct KPeakTables {
     typedef PeakTabParams Params;
+    static const char* name() { return "peak_tables"; }
     static constexpr int NT = 256, MINB = 4, NPH = 2, NSUM = 1;
     struct Regs { u64 key; double dsum[NSUM]; };
     static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }
@@ -217,6 +220,7 @@ struct PeakSumParams {
 };
 template <int L1MAX> struct KPeakSums {
     typedef PeakSumParams Params;
+    static const char* name() { return "peak_sums"; }
     static constexpr int KW = 16;                 // k2 columns per CTA
     static constexpr int NT = 256, MINB = 2, NPH = 3, NSUM = 2 * PEAK_NPTS;
     static constexpr int NGRP = NT / KW;
@@ -291,6 +295,7 @@ struct PeakFinParams {
 };
 struct KPeakFinal {
     typedef PeakFinParams Params;
+    static const char* name() { return "peak_final"; }
     static constexpr int NT = 256, MINB = 4, NPH = 2, NSUM = 2 * PEAK_NPTS + 1;
     struct Regs { u64 key; double dsum[NSUM]; };
     static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }
@@ -385,6 +390,7 @@ struct PrnParams {
 };
 struct KPrnGen {
     typedef PrnParams Params;
+    static const char* name() { return "prn_gen"; }
     static constexpr int NT = 128, MINB = 4, NPH = 1, NSUM = 1, CH = 64;
     struct Regs { u64 key; double dsum[NSUM]; };
     static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }

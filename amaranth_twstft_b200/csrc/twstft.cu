@@ -428,6 +428,39 @@ int twstft_synchronize(twstft_plan* p)
     p->be.sync();
     return p->be.ok() ? TWSTFT_OK : fail(p, TWSTFT_E_CUDA, p->be.err_string());
 }
+int twstft_timer_start(twstft_plan* p)
+{
+    if (!p) return TWSTFT_E_ARG;
+    p->be.use();
+    p->be.timer_start();
+    return TWSTFT_OK;
+}
+int twstft_timer_stop(twstft_plan* p, float* ms)
+{
+    if (!p || !ms) return TWSTFT_E_ARG;
+    p->be.use();
+    *ms = p->be.timer_stop();
+    return p->be.ok() ? TWSTFT_OK : fail(p, TWSTFT_E_CUDA, p->be.err_string());
+}
+int twstft_profile_enable(twstft_plan* p, int on)
+{
+    if (!p) return TWSTFT_E_ARG;
+    p->be.use();
+    if (!on) p->be.prof_collect();
+    p->be.profiling = on != 0;
+    return TWSTFT_OK;
+}
+int twstft_profile_read(twstft_plan* p, int slot, char* name, size_t name_cap, double* total_ms, int64_t* count)
+{
+    if (!p) return TWSTFT_E_ARG;
+    p->be.use();
+    p->be.prof_collect();
+    if (slot < 0 || slot >= (int)p->be.prof.size()) return 1;   /* end of list */
+    if (name && name_cap) { strncpy(name, p->be.prof[slot].name, name_cap - 1); name[name_cap - 1] = 0; }
+    if (total_ms) *total_ms = p->be.prof[slot].ms;
+    if (count) *count = p->be.prof[slot].count;
+    return TWSTFT_OK;
+}
 int twstft_debug_fetch(twstft_plan* p, int what, int lane, void* host_out, size_t bytes)
 {
     if (!p || !p->pipe) return TWSTFT_E_ARG;

@@ -1,0 +1,291 @@
+#!/usr/bin/env python3
+"""Benchmark of the per-second PRN correlator hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one pass of the hot path (carrier estimate -> derotate -> correlate x3 -> peak /
+fine delay / phase / SNR) over one batch of RECORDS_PER_STEP synthetic two-channel 1-s records
+(5 MS/s, 2.5 Mchip/s BPSK, 22-bit taps-3 LFSR code: BASELINE.json configs[1]).
+  value  records/s over all GPUs with the records already resident in HBM (twstft_process_device)
+  e2e    the same metric through twstft_process with HOST (pinned) records, H2D + D2H in the timed region
+  roofline   dominant kernel: algorithmic bytes per launch / CUDA-event duration vs the measured HBM peak
+  cpu_baseline  the numpy oracle (a port of godual_ranging.m) on one host core, one record
+--impl reference times the oracle port on all host cores (the reference's Octave/C++ cannot be built here).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N = 5000000
+FS = 5e6
+CODE = (22, 3, 2500000)          # bitlen, taps, noiselen (experiments/221207_twoway_codes/codes/noiselen2500000_bitlen22_taps03)
+RECORDS_PER_STEP = 8
+METRIC = "two-channel 1-s 5 MS/s records correlated per second"
+UNIT = "records/s"
+SURVEY_BYTES_PER_RECORD = 1.4e9  # 140*N bytes per channel, two channels
+# algorithmic bytes per lane (one channel of one record) and launch, in units of N bytes
+ALG_BYTES_N = {"mean": 4, "col_fwd_raw": 12, "row_fwd_argmax": 8, "row_fwd_mulcode": 24,
+               "row_inv_twist": 32, "col_inv_argmax": 24, "peak_sums": 8}
+
+
+def measured_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def make_records(code, seeds):
+    from amaranth_twstft_b200 import synth
+    return [synth.record_pair(code, s, fs=FS)[0] for s in seeds]
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def oracle_record(raw, code):
+    from oracle import correlator as oc
+    freq = oc.freq_axis_G(FS, N)
+    k = oc.window(freq, -20000.0, 20000.0)
+    return oc.record_G(raw, k, freq, oc.fcode_G(code), code, fs=FS)
+
+
+def _ref_worker(args):
+    seed, = args
+    from oracle import correlator as oc
+    from oracle import prn
+    from amaranth_twstft_b200 import synth
+    code = oc.code_bpsk(prn.lfsr_bits(*CODE))
+    raw, _ = synth.record_pair(code, seed, fs=FS)
+    freq = oc.freq_axis_G(FS, N)
+    k = oc.window(freq, -20000.0, 20000.0)
+    fcode = oc.fcode_G(code)
+    t0 = time.perf_counter()
+    oc.record_G(raw, k, freq, fcode, code, fs=FS, channels=(1,))     # ONE channel = half a record
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """Reference arm: the oracle port of godual_ranging.m on all usable host cores (Octave and the
+    C++/FFTW port cannot be built in this image).  One step = `workers` channel-correlations in
+    parallel (half a record each), sized so that K+W steps end within a few minutes."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    workers = max(1, min(os.cpu_count() or 1, 32))
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(workers) as pool:
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            pool.map(_ref_worker, [(20261017 + step * workers + i,) for i in range(workers)])
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    value = 0.5 * workers * len(times) / total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1]: two-channel 1-s 5 MS/s BPSK records, 22-bit taps-3 code, x3 interpolation",
+                       "records_per_step": 0.5 * workers},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
+                             "sample": f"{workers} single-channel correlations (half records) per step, numpy oracle "
+                                       "port of processing/Octave/godual_ranging.m, one process per core"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--records-per-step", type=int, default=RECORDS_PER_STEP)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    from amaranth_twstft_b200.api import Correlator
+    R = args.records_per_step
+    cor = Correlator(nsamples=N, fs=FS, max_batch=R, device=local)
+    assert cor.backend == "cuda"
+    bits = cor.gen_code(CODE[0], CODE[1])
+    code = 2.0 * np.repeat(bits.astype(np.float64), 2) - 1.0
+    # resident pool: R distinct records per rank (R*40 MB >> 126 MB L2 for R >= 4)
+    recs = make_records(code, [20261017 + rank * 1000 + i for i in range(R)])
+    rec_bytes = recs[0].nbytes
+    pinned = cor.pinned_empty(R * rec_bytes)
+    host = pinned.view(np.int16)
+    for i, r in enumerate(recs):
+        host[i * r.size:(i + 1) * r.size] = r
+    dev = cor.to_device(host)
+
+    for _ in range(max(args.warmup, 3)):
+        res = cor.process_device(dev, R)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    l0 = cor.kernel_launches
+    cor.timer_start()
+    for _ in range(args.steps):
+        res = cor.process_device(dev, R)
+    ms = cor.timer_stop()
+    launches = cor.kernel_launches - l0
+    barrier()
+    clocks = sampler.stop()
+    ms = max_over_ranks(ms)
+    value = world * R * args.steps / (ms * 1e-3)
+
+    # end to end: host (pinned) records in, results out, copies inside the timed region
+    for _ in range(2):
+        cor.process(host)
+    barrier()
+    cor.timer_start()
+    e2e_steps = max(3, args.steps // 2)
+    for _ in range(e2e_steps):
+        res_e2e = cor.process(host)
+    ms_e2e = max_over_ranks(cor.timer_stop())
+    e2e_value = world * R * e2e_steps / (ms_e2e * 1e-3)
+    barrier()
+
+    # per-kernel durations (CUDA events around every launch, two extra steps)
+    cor.profile(True)
+    for _ in range(2):
+        cor.process_device(dev, R)
+    cor.profile(False)
+    prof = cor.profile_read()
+    peak, peak_kind = measured_peak()
+    kernels = {}
+    for name, (tot_ms, cnt) in prof.items():
+        avg = tot_ms / max(cnt, 1)
+        ent = {"avg_ms": avg, "launches": cnt, "share": None}
+        if name in ALG_BYTES_N:
+            b = ALG_BYTES_N[name] * N * 2 * R
+            ent["alg_bytes"] = b
+            ent["gbs"] = b / (avg * 1e-3) / 1e9
+            ent["frac"] = ent["gbs"] / peak
+        kernels[name] = ent
+    tot = sum(v[0] for v in prof.values()) or 1.0
+    for name in kernels:
+        kernels[name]["share"] = prof[name][0] / tot
+    dom = max((k for k in kernels if "gbs" in kernels[k]), key=lambda k: prof[k][0], default=None)
+    roofline = None
+    if dom:
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": kernels[dom]["frac"], "traffic": None, "peak_kind": peak_kind,
+                    "share_of_step": kernels[dom]["share"]}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: two-channel 1-s 5 MS/s BPSK records, 22-bit taps-3 code, x3 interpolation",
+                       "records_per_step": R, "samples_per_record": N, "l2": f"inputs larger than L2: {R} distinct "
+                       f"records = {R * rec_bytes / 1e6:.0f} MB raw, {R * 2 * 200:.0f} MB intermediates per step"},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": R * rec_bytes,
+                    "d2h_bytes_per_step": int(res_e2e.nbytes)},
+            "roofline": roofline, "kernels": kernels,
+            "pipeline": {"alg_bytes_per_record": sum(ALG_BYTES_N.values()) * N * 2,
+                         "frac_of_hbm_peak": value / world * sum(ALG_BYTES_N.values()) * N * 2 / 1e9 / peak,
+                         "survey_bytes_per_record": SURVEY_BYTES_PER_RECORD,
+                         "frac_of_hbm_peak_survey_bytes": value / world * SURVEY_BYTES_PER_RECORD / 1e9 / peak}}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        t0 = time.perf_counter()
+        ref = oracle_record(recs[0], code)
+        dt = time.perf_counter() - t0
+        ok = all(int(res[0, ch - 1]["indice"]) == ref[ch]["indice"] and
+                 abs(res[0, ch - 1]["correction"] - ref[ch]["correction"]) < 3e-4 for ch in (1, 2))
+        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "1 two-channel record (2 channel-correlations) through the numpy oracle "
+                                          "port of processing/Octave/godual_ranging.m, single process",
+                                "parity_with_gpu_on_sample": "ok" if ok else "MISMATCH"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    cor.device_free(dev)
+    cor.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

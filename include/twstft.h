@@ -125,6 +125,13 @@ int twstft_copy_to_device(twstft_plan* plan, void* dst_dev, const void* src_host
 int twstft_copy_to_host(twstft_plan* plan, void* dst_host, const void* src_dev, size_t bytes);
 int twstft_synchronize(twstft_plan* plan);
 
+/* Device-side timing on the plan's own stream (CUDA events), used by bench.py.
+ * twstft_profile_*: one event pair per kernel launch, accumulated per kernel type. */
+int twstft_timer_start(twstft_plan* plan);
+int twstft_timer_stop(twstft_plan* plan, float* ms);
+int twstft_profile_enable(twstft_plan* plan, int on);
+int twstft_profile_read(twstft_plan* plan, int slot, char* name, size_t name_cap, double* total_ms, int64_t* count);
+
 /* Introspection used by tests and the benchmark. */
 int64_t twstft_kernel_launches(const twstft_plan* plan);   /* kernels launched so far by this plan */
 int twstft_debug_fetch(twstft_plan* plan, int what, int lane, void* host_out, size_t bytes);

@@ -48,6 +48,12 @@ struct Backend {
     void h2d(void* d, const void* h, size_t bytes) { memcpy(d, h, bytes); }
     void d2h(void* h, const void* d, size_t bytes) { memcpy(h, d, bytes); }
     void sync() {}
+    struct ProfSlot { const char* name; double ms; long count; };
+    bool profiling = false;
+    std::vector<ProfSlot> prof;
+    void prof_collect() {}
+    void timer_start() {}
+    float timer_stop() { return 0.f; }
     template <class K> void launch(dim3 grid, const typename K::Params& p)
     {
         std::vector<unsigned char> smem(K::smem_bytes() + 64);

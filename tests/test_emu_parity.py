@@ -1,0 +1,154 @@
+"""CPU checks of the CUDA kernels' arithmetic: the kernel phase functions compiled for the host
+(tests/emu, test-only) are run through the same C ABI and compared with the oracle.  These are the
+'host logic' tests; the parity tests proper run on the GPU (test_gpu_parity.py)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import parity_common as pc
+from amaranth_twstft_b200 import synth
+from amaranth_twstft_b200.api import Correlator
+from oracle import correlator as oc
+from oracle import prn
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+needs_emu = pytest.mark.skipif(not os.path.exists(pc.EMU_LIB), reason="emulation library not built")
+pytestmark = needs_emu
+
+
+@pytest.mark.parametrize("n", [10000, 200000, 250000])
+def test_variant_g(n):
+    pc.run_variant_g(pc.EMU_LIB, n, seeds=[11, 12, 13])
+
+
+def test_variant_g_1e6():
+    pc.run_variant_g(pc.EMU_LIB, 1000000, seeds=[11])
+
+
+@pytest.mark.slow
+def test_variant_g_full_size_record():
+    pc.run_variant_g(pc.EMU_LIB, 5000000, seeds=[20261017], max_batch=1)
+
+
+@pytest.mark.parametrize("entry", [e for e in json.load(open(os.path.join(G, "prn_digests.json")))
+                                   if e["noiselen"] <= 500000], ids=lambda e: os.path.basename(e["file"]))
+def test_lfsr_kernel_matches_reference_files(entry):
+    from amaranth_twstft_b200 import _lib
+    lib = _lib.load(pc.EMU_LIB)
+    n = entry["noiselen"]
+    out = np.zeros(n, dtype=np.uint8)
+    assert lib.twstft_prn_generate(0, entry["bitlen"], entry["taps_a"], 0, 1, n, out.ctypes.data) == 0
+    assert hashlib.sha256(out.tobytes()).hexdigest() == entry["sha256"]
+
+
+def test_lfsr_kernel_qpsk_interleave_and_seed():
+    from amaranth_twstft_b200 import _lib
+    lib = _lib.load(pc.EMU_LIB)
+    out = np.zeros(2 * 1000, dtype=np.uint8)
+    assert lib.twstft_prn_generate(0, 17, 9, 15, 5, 1000, out.ctypes.data) == 0
+    assert (out == prn.prn_file_bytes(17, 1000, 9, 15, seed=5)).all()
+
+
+@pytest.mark.parametrize("axis,lo,hi,n", [("G", -20000, 20000, 5000000), ("G", 80000, 120000, 5000000),
+                                          ("G", -120000, -80000, 5000000), ("K", 100000, 120000, 200000),
+                                          ("K", -8000, 8000, 200000), ("G", -20000, 20000, 10000)])
+def test_window_bins_equal_octave_find(axis, lo, hi, n):
+    fs = 5e6
+    freq = oc.freq_axis_G(fs, n) if axis == "G" else np.linspace(-fs / 2, fs / 2 - 1.0, n)
+    k = oc.window(freq, lo, hi)
+    with Correlator(nsamples=n, fs=fs, window_hz=(lo, hi), freq_axis=axis, max_batch=1, lib=pc.EMU_LIB) as cor:
+        assert cor.window_bins() == (k[0], k[-1])
+
+
+def test_remote_window_and_negative_offset():
+    """remote channel: carrier in the 80-120 kHz window of the x^2 spectrum (godual_ranging.m:82-90)."""
+    pc.run_variant_g(pc.EMU_LIB, 250000, seeds=[5], window=(80000.0, 120000.0),
+                     overrides=dict(ch1=dict(df=51234.5), ch2=dict(df=49000.25)))
+    pc.run_variant_g(pc.EMU_LIB, 250000, seeds=[6], window=(-120000.0, -80000.0),
+                     overrides=dict(ch1=dict(df=-51234.5), ch2=dict(df=-43000.0)))
+
+
+def test_batching_is_transparent():
+    """7 records through max_batch=3 == the same records one by one."""
+    bits, code = pc.make_code(10000)
+    recs = np.stack([synth.record_pair(code, s)[0] for s in range(30, 37)])
+    with Correlator(nsamples=10000, max_batch=3, lib=pc.EMU_LIB) as cor:
+        cor.set_code(bits)
+        a = cor.process(recs)
+    with Correlator(nsamples=10000, max_batch=1, lib=pc.EMU_LIB) as cor:
+        cor.set_code(bits)
+        b = np.concatenate([cor.process(r) for r in recs])
+    for nm in a.dtype.names:
+        assert np.array_equal(a[nm], b[nm]), nm
+
+
+def _k_case(n, seed, delay, df, snr_db=-5.0):
+    bits, code = pc.make_code(n)
+    raw, tr = synth.record_single(code, seed, delay=delay, df=df, snr_db=snr_db)
+    return bits, code, raw
+
+
+@pytest.mark.parametrize("delay", [0.0, 0.2, 1.0 / 3.0, 17.4, 4321.7, 9999.6])
+def test_variant_k_windows(delay):
+    """processing(d,k,df) of claudio_aligned_code_lo_separate.m:24-77 incl. the neighbour-wrap quirks."""
+    n = 10000
+    bits, code, raw = _k_case(n, 77, delay, 1234.5)
+    df = 1234.5
+    with Correlator(nsamples=n, variant="K", layout="single", max_batch=2, lib=pc.EMU_LIB) as cor:
+        cor.set_code(bits)
+        res = cor.process_windows(raw, [0], [df])
+    d = oc.unpack_single(raw)
+    ref = oc.processing_K(d - d.mean(), df, oc.fcode_K(code), code)
+    pc.assert_row_matches(res[0, 0], ref, where=f"K delay={delay}")
+
+
+def test_variant_k_window_offsets_in_long_buffer():
+    """Windows at arbitrary sample offsets of a longer single-channel buffer (dindex tracking, A11)."""
+    n = 10000
+    bits, code = pc.make_code(n)
+    parts = [synth.record_single(code, 90 + i, delay=21.3, df=-777.0)[0] for i in range(3)]
+    raw = np.concatenate(parts)
+    offs = [0, 5, n - 3, 2 * n]
+    with Correlator(nsamples=n, variant="K", layout="single", max_batch=3, lib=pc.EMU_LIB) as cor:
+        cor.set_code(bits)
+        res = cor.process_windows(raw, offs, [-777.0] * len(offs))
+    d = oc.unpack_single(raw)
+    for i, o in enumerate(offs):
+        w = d[o:o + n]
+        ref = oc.processing_K(w - w.mean(), -777.0, oc.fcode_K(code), code)
+        pc.assert_row_matches(res[i, 0], ref, where=f"K offset={o}")
+
+
+def test_variant_g_peak_at_array_edge_sets_status():
+    """godual_ranging.m:31-32 would index out of range when the peak is the first/last sample; the
+    library wraps and raises bit0 of status instead."""
+    n = 10000
+    bits, code = pc.make_code(n)
+    raw, _ = synth.record_pair(code, 5, ch1=dict(delay=0.0, snr_db=10.0), ch2=dict(delay=n - 1.0 / 3.0, snr_db=10.0))
+    with Correlator(nsamples=n, max_batch=1, lib=pc.EMU_LIB) as cor:
+        cor.set_code(bits)
+        res = cor.process(raw)
+    assert int(res[0, 0]["indice"]) == 1 and int(res[0, 0]["status"]) & 1
+    assert int(res[0, 1]["indice"]) == 3 * n and int(res[0, 1]["status"]) & 1
+    freq = oc.freq_axis_G(5e6, n)
+    ref = oc.record_G(raw, oc.window(freq, -20000, 20000), freq, oc.fcode_G(code), code)
+    pc.assert_row_matches(res[0, 0], ref[1], where="edge ch1")
+    pc.assert_row_matches(res[0, 1], ref[2], where="edge ch2")
+
+
+def test_estimate_carrier_only():
+    n = 250000
+    bits, code = pc.make_code(n)
+    recs = np.stack([synth.record_pair(code, s)[0] for s in (1, 2)])
+    with Correlator(nsamples=n, max_batch=2, lib=pc.EMU_LIB) as cor:
+        df, bins = cor.estimate_carrier(recs)
+    freq = oc.freq_axis_G(5e6, n)
+    k = oc.window(freq, -20000, 20000)
+    for i in range(2):
+        d1, d2 = oc.unpack_interleaved2(recs[i])
+        for ch, d in enumerate((d1, d2)):
+            s, f = oc.carrier_estimate(d - d.mean(), k, freq)
+            assert bins[i, ch] == s and df[i, ch] == f
