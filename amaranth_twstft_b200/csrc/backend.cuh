@@ -24,6 +24,7 @@ struct Backend {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     int device = 0;
+    int num_sms = 148;
     cudaError_t err = cudaSuccess;
     long launches = 0;
 
@@ -39,6 +40,7 @@ struct Backend {
         if (dev < 0 || dev >= n) { err = cudaErrorInvalidDevice; return -1; }
         device = dev;
         note(cudaSetDevice(dev));
+        note(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         note(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         note(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
         return ok() ? 0 : -1;

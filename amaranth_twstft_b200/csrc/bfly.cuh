@@ -90,10 +90,41 @@ template <int RA, int RB> struct BflyCT {
     }
 };
 
+// R = RA*RB with gcd(RA,RB)=1: Good-Thomas prime-factor algorithm, no internal twiddles.
+//   input  n = (RB*n1 + RA*n2) mod R,  output k = (RB*IB*k1 + RA*IA*k2) mod R
+//   IB = RB^-1 mod RA, IA = RA^-1 mod RB  (index maps are compile-time register renames)
+template <int RA, int RB, int IB, int IA> struct BflyPFA {
+    static HD void run(float2* v)
+    {
+        constexpr int R = RA * RB;
+        static_assert((RB * IB) % RA == 1 % RA && (RA * IA) % RB == 1 % RB, "CRT inverses");
+        float2 t[RA][RB];
+#pragma unroll
+        for (int n1 = 0; n1 < RA; n1++)
+#pragma unroll
+            for (int n2 = 0; n2 < RB; n2++) t[n1][n2] = v[(RB * n1 + RA * n2) % R];
+#pragma unroll
+        for (int n2 = 0; n2 < RB; n2++) {
+            float2 c[RA];
+#pragma unroll
+            for (int n1 = 0; n1 < RA; n1++) c[n1] = t[n1][n2];
+            Bfly<RA>::run(c);
+#pragma unroll
+            for (int k1 = 0; k1 < RA; k1++) t[k1][n2] = c[k1];
+        }
+#pragma unroll
+        for (int k1 = 0; k1 < RA; k1++) {
+            Bfly<RB>::run(t[k1]);
+#pragma unroll
+            for (int k2 = 0; k2 < RB; k2++) v[(RB * IB * k1 + RA * IA * k2) % R] = t[k1][k2];
+        }
+    }
+};
+
 template <> struct Bfly<8> { static HD void run(float2* v) { BflyCT<2, 4>::run(v); } };
-template <> struct Bfly<10> { static HD void run(float2* v) { BflyCT<2, 5>::run(v); } };
+template <> struct Bfly<10> { static HD void run(float2* v) { BflyPFA<2, 5, 1, 3>::run(v); } };
 template <> struct Bfly<16> { static HD void run(float2* v) { BflyCT<4, 4>::run(v); } };
-template <> struct Bfly<20> { static HD void run(float2* v) { BflyCT<4, 5>::run(v); } };
+template <> struct Bfly<20> { static HD void run(float2* v) { BflyPFA<4, 5, 1, 4>::run(v); } };
 template <> struct Bfly<25> { static HD void run(float2* v) { BflyCT<5, 5>::run(v); } };
 
 }  // namespace twstft

@@ -19,7 +19,7 @@ namespace twstft {
 typedef unsigned long long u64;
 typedef long long i64;
 
-struct Blk { int x, y, z; };
+struct Blk { int x, y, z, gx; };   // block index and gridDim.x
 
 enum SyncKind { SYNC_BARRIER = 0, SYNC_MAXKEY = 1, SYNC_SUMD = 2, SYNC_MAXKEY_SUMD = 3 };
 
@@ -71,6 +71,32 @@ HD double2 cis_cycles_d(double c)
 }
 
 HD double2 dmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// Asynchronous global->shared copies (LDGSTS).  On the host (test emulation) they complete at once.
+HD void cp_async8(void* smem_dst, const void* gsrc)
+{
+#ifdef __CUDA_ARCH__
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc) : "memory");
+#else
+    *reinterpret_cast<float2*>(smem_dst) = *reinterpret_cast<const float2*>(gsrc);
+#endif
+}
+HD void cp_async4(void* smem_dst, const void* gsrc)
+{
+#ifdef __CUDA_ARCH__
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc) : "memory");
+#else
+    *reinterpret_cast<int*>(smem_dst) = *reinterpret_cast<const int*>(gsrc);
+#endif
+}
+HD void cp_async_wait_all()
+{
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+#endif
+}
 
 // Order-preserving key for "first maximum": larger value wins, then SMALLER index.
 HD u64 make_key(float v, unsigned idx)

@@ -1,19 +1,21 @@
-// Shared-memory Stockham FFT building blocks (forward transform, radices 2/4/5 and composites).
+// Shared-memory FFT building blocks: in-place decimation-in-frequency, radices 2/4/5 and composites.
 //
-// A transform of length L = R0*R1*R2 is run by NTS = L/max(R) threads, each owning E = max(R)
-// elements in registers.  Stage s (radix R, Ns = product of the earlier radices) does, for
-// butterfly index jb in [0, L/R):
-//     v[m]  = X[jb + m*L/R] * W_{Ns*R}^{(jb mod Ns)*m}        m = 0..R-1
-//     v     = DFT_R(v)
-//     Y[(jb/Ns)*Ns*R + (jb mod Ns) + m*Ns] = v[m]
-// (autosort: natural order in, natural order out, no digit reversal).  The first stage reads global
-// memory directly (coalesced: consecutive jb), the last stage writes global memory directly
-// (index jb + m*L/R, coalesced again); only the exchanges in between go through shared memory.
+// A forward transform of length L = R0*R1*R2 is run by NTS = L/max(R) threads, each owning
+// E = max(R) elements in registers.  With the index written in mixed radix
+//     i = i0*(R1*R2) + i1*R2 + i2,        k = k0 + R0*k1 + R0*R1*k2,
+// stage 0 transforms over i0 (stride R1*R2) and multiplies output k0 by W_L^{k0*(i1*R2+i2)},
+// stage 1 transforms over i1 (stride R2)    and multiplies output k1 by W_{R1*R2}^{k1*i2},
+// stage 2 transforms over i2 (stride 1).
+// Every butterfly writes its outputs to the very slots it read (digit i_s replaced by k_s), so a
+// stage needs only ONE block barrier (before the next stage's reads) and its stores overlap its
+// arithmetic.  The first stage reads global memory directly (index jb + m*L/R0: coalesced), the last
+// stage is visited as (output index jb + m*L/RLAST, value): natural order, coalesced again.
 //
-// Stage twiddles come from small 2-D tables laid out [m][k] so that consecutive threads read
-// consecutive words (no bank conflicts); for Ns > 32, k = KD*kh + kl and the twiddle is the product
-// TA[m][kh] * TB[m][kl] (two correctly-rounded factors, error ~1e-7).  The tables ("blob") are
-// computed in fp64 on the host once per plan and copied into shared memory by every CTA.
+// Stage twiddles are powers w^m of one per-butterfly root w.  Only the seeds w^1..w^(B-1) and
+// w^B, w^2B, ... (B = 5 or 4) come from tables; the rest are products of two seeds (error ~2e-7).
+// Tables are laid out [seed][k] so that consecutive threads read consecutive words; when the
+// root index k exceeds 32 values it is split k = KD*kh + kl and the seed is TA[.][kh]*TB[.][kl].
+// The tables ("blob") are computed in fp64 on the host once per plan.
 //
 // Inverse transforms use the same code through IDFT(x) = swap(DFT(swap(x))), swap = (re<->im).
 #pragma once
@@ -30,6 +32,15 @@ constexpr int split_kd(int ns)
 }
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
+// seeds of a radix-R stage: w^1..w^(B-1), w^B, w^2B, ..., w^(R-B)
+template <int R> struct Seeds {
+    static constexpr int B = (R <= 5) ? R : ((R % 5 == 0) ? 5 : 4);
+    static constexpr int NLOW = B - 1;                 // w^1..w^(B-1)
+    static constexpr int NHIGH = R / B - 1;            // w^B..w^(R-B)
+    static constexpr int N = NLOW + NHIGH;
+    static constexpr int exponent(int row) { return row < NLOW ? row + 1 : B * (row - NLOW + 1); }
+};
+
 template <int R0_, int R1_ = 1, int R2_ = 1> struct FFTSpec {
     static constexpr int R0 = R0_, R1 = R1_, R2 = R2_;
     static_assert(R1 > 1 || R2 == 1, "stages must be packed to the front");
@@ -38,100 +49,149 @@ template <int R0_, int R1_ = 1, int R2_ = 1> struct FFTSpec {
     static constexpr int RMAX = cmax(R0, cmax(R1, R2));
     static constexpr int NTS = L / RMAX;          // threads per sequence
     static constexpr int E = RMAX;                // elements per thread
-    static_assert((L / R0) % NTS == 0 && (L / R1) % NTS == 0 && (L / R2) % NTS == 0 || R1 == 1,
+    static_assert((L / R0) % NTS == 0 && (L / R1) % NTS == 0 && (L / R2) % NTS == 0,
                   "thread count must divide the butterfly count of every stage");
     static constexpr int RLAST = R2 > 1 ? R2 : (R1 > 1 ? R1 : R0);
     static constexpr int NSLAST = L / RLAST;      // output index of the last stage: jb + m*NSLAST
-    // stage 1 tables
-    static constexpr int NS1 = R0, KD1 = split_kd(NS1), KH1 = NS1 / KD1;
-    static constexpr int NS2 = R0 * R1, KD2 = split_kd(NS2), KH2 = NS2 / KD2;
-    static constexpr int OFF_B1 = 0;
-    static constexpr int OFF_A1 = OFF_B1 + (R1 > 1 ? R1 * KD1 : 0);
-    static constexpr int OFF_B2 = OFF_A1 + ((R1 > 1 && KH1 > 1) ? R1 * KH1 : 0);
-    static constexpr int OFF_A2 = OFF_B2 + (R2 > 1 ? R2 * KD2 : 0);
-    static constexpr int BLOB = OFF_A2 + ((R2 > 1 && KH2 > 1) ? R2 * KH2 : 0);   // float2 entries
+    static constexpr int SP0 = R1 * R2;           // stride of digit i0 (= butterflies in stage 0)
+    // stage-0 twiddle tables: root index jb in [0, SP0)
+    static constexpr int KD0 = split_kd(SP0), KH0 = SP0 / KD0;
+    static constexpr int NSEED0 = Seeds<R0>::N, NSEED1 = Seeds<R1>::N;
+    static constexpr int OFF_B0 = 0;
+    static constexpr int OFF_A0 = OFF_B0 + (NSTAGE > 1 ? NSEED0 * KD0 : 0);
+    // middle-stage twiddle table (3 stages only): root index i2 in [0, R2), R2 <= 32
+    static constexpr int OFF_B1 = OFF_A0 + ((NSTAGE > 1 && KH0 > 1) ? NSEED0 * KH0 : 0);
+    static constexpr int BLOB = OFF_B1 + (NSTAGE == 3 ? NSEED1 * R2 : 0);     // float2 entries
     static constexpr int BLOB_PAD = (BLOB + 1) & ~1;
-};
-
-template <class S, int STAGE> struct StageInfo;
-template <class S> struct StageInfo<S, 0> {
-    static constexpr int R = S::R0, NS = 1, KD = 1, KH = 1, OFF_B = 0, OFF_A = 0;
-};
-template <class S> struct StageInfo<S, 1> {
-    static constexpr int R = S::R1, NS = S::NS1, KD = S::KD1, KH = S::KH1, OFF_B = S::OFF_B1, OFF_A = S::OFF_A1;
-};
-template <class S> struct StageInfo<S, 2> {
-    static constexpr int R = S::R2, NS = S::NS2, KD = S::KD2, KH = S::KH2, OFF_B = S::OFF_B2, OFF_A = S::OFF_A2;
+    static_assert(NSTAGE < 3 || R2 <= 32, "middle-stage root table is unsplit");
 };
 
 // Host: fill the twiddle blob of a spec (fp64 -> fp32).
 template <class S> void fill_blob(float2* out)
 {
     const double TWO_PI = 6.283185307179586476925287;
-    auto fill = [&](int R, int NS, int KD, int KH, int offB, int offA) {
-        if (R <= 1) return;
-        double M = (double)NS * R;
-        for (int m = 0; m < R; m++)
-            for (int kl = 0; kl < KD; kl++) {
-                double a = -TWO_PI * (double)(kl * m) / M;
-                out[offB + m * KD + kl] = make_float2((float)cos(a), (float)sin(a));
+    if (S::NSTAGE > 1) {
+        for (int row = 0; row < S::NSEED0; row++) {
+            const int m = Seeds<S::R0>::exponent(row);
+            for (int kl = 0; kl < S::KD0; kl++) {
+                double a = -TWO_PI * (double)((long long)m * kl) / (double)S::L;
+                out[S::OFF_B0 + row * S::KD0 + kl] = make_float2((float)cos(a), (float)sin(a));
             }
-        if (KH > 1)
-            for (int m = 0; m < R; m++)
-                for (int kh = 0; kh < KH; kh++) {
-                    double a = -TWO_PI * (double)((long long)KD * kh * m) / M;
-                    out[offA + m * KH + kh] = make_float2((float)cos(a), (float)sin(a));
+            if (S::KH0 > 1)
+                for (int kh = 0; kh < S::KH0; kh++) {
+                    double a = -TWO_PI * (double)((long long)m * S::KD0 * kh) / (double)S::L;
+                    out[S::OFF_A0 + row * S::KH0 + kh] = make_float2((float)cos(a), (float)sin(a));
                 }
-    };
-    fill(S::R1, S::NS1, S::KD1, S::KH1, S::OFF_B1, S::OFF_A1);
-    fill(S::R2, S::NS2, S::KD2, S::KH2, S::OFF_B2, S::OFF_A2);
+        }
+    }
+    if (S::NSTAGE == 3) {
+        for (int row = 0; row < S::NSEED1; row++) {
+            const int m = Seeds<S::R1>::exponent(row);
+            for (int i2 = 0; i2 < S::R2; i2++) {
+                double a = -TWO_PI * (double)(m * i2) / (double)(S::R1 * S::R2);
+                out[S::OFF_B1 + row * S::R2 + i2] = make_float2((float)cos(a), (float)sin(a));
+            }
+        }
+    }
 }
 
-// One stage, first half: gather R inputs per butterfly through `src(index)`, apply the stage
-// twiddles from the (shared-memory) blob `tw`, run the butterflies.  j = thread index in [0,NTS).
-template <class S, int STAGE, class Src> HD void stage_compute(int j, float2* v, const float2* tw, Src src)
+// Multiply outputs v[1..R-1] of a butterfly by w^m, the seeds read through `seed(row)`.
+template <int R, class SeedFn> HD void apply_powers(float2* v, SeedFn seed)
 {
-    typedef StageInfo<S, STAGE> I;
-    constexpr int R = I::R, NS = I::NS, KD = I::KD, KH = I::KH;
-    constexpr int NBF = S::L / R;            // butterflies in this stage
-    constexpr int NB = NBF / S::NTS;         // butterflies per thread
+    typedef Seeds<R> SD;
+    float2 lo[SD::NLOW > 0 ? SD::NLOW : 1];
+#pragma unroll
+    for (int b = 1; b < SD::B; b++) {
+        lo[b - 1] = seed(b - 1);
+        v[b] = cmul(v[b], lo[b - 1]);
+    }
+#pragma unroll
+    for (int a = 1; a <= SD::NHIGH; a++) {
+        const float2 hi = seed(SD::NLOW + a - 1);
+        v[a * SD::B] = cmul(v[a * SD::B], hi);
+#pragma unroll
+        for (int b = 1; b < SD::B; b++) v[a * SD::B + b] = cmul(v[a * SD::B + b], cmul(hi, lo[b - 1]));
+    }
+}
+
+// Exchange-buffer layouts.  at(block, within): `block` = most significant digit (0..R0-1),
+// `within` in [0, SP0).  unit() = pointer stride of one `within` step.
+//   RowAcc: one sequence, each block padded so that the block stride is odd (conflict-free last stage)
+//   ColAcc: TS interleaved sequences, element p of sequence s at data[p*TS + s]
+template <int SP0> struct RowAcc {
+    static constexpr int BSTRIDE = SP0 + ((SP0 % 2 == 0) ? 5 : 4);
+    float2* data;
+    HD float2* at(int block, int within) const { return data + block * BSTRIDE + within; }
+    static constexpr int unit() { return 1; }
+    static constexpr int bstride() { return BSTRIDE; }
+};
+template <int SP0, int TS> struct ColAcc {
+    float2* data;   // already offset by s
+    HD float2* at(int block, int within) const { return data + (block * SP0 + within) * TS; }
+    static constexpr int unit() { return TS; }
+    static constexpr int bstride() { return SP0 * TS; }
+};
+
+// ---- stage 0: butterflies over the most significant digit; v[b*R0+m] = x[jb + m*SP0] on entry ----
+template <class S, class Acc> HD void dif_stage0(int j, float2* v, const float2* tw, const Acc& acc)
+{
+    constexpr int R = S::R0, NB = S::SP0 / S::NTS;
 #pragma unroll
     for (int b = 0; b < NB; b++) {
         const int jb = j + S::NTS * b;
         float2* vb = v + b * R;
+        Bfly<R>::run(vb);
+        if (S::NSTAGE > 1) {
+            const float2* tb = tw + S::OFF_B0 + jb % S::KD0;
+            const float2* ta = tw + S::OFF_A0 + jb / S::KD0;
+            apply_powers<R>(vb, [&](int row) {
+                float2 w = tb[row * S::KD0];
+                if (S::KH0 > 1) w = cmul(w, ta[row * S::KH0]);
+                return w;
+            });
+            float2* p = acc.at(0, jb);
 #pragma unroll
-        for (int m = 0; m < R; m++) vb[m] = src(jb + m * NBF);
-        if (NS > 1) {
-            const int k = jb % NS;
-            const int kl = k % KD, kh = k / KD;
-#pragma unroll
-            for (int m = 1; m < R; m++) {
-                float2 w = tw[I::OFF_B + m * KD + kl];
-                if (KH > 1) w = cmul(w, tw[I::OFF_A + m * KH + kh]);
-                vb[m] = cmul(vb[m], w);
-            }
+            for (int m = 0; m < R; m++) p[m * Acc::bstride()] = vb[m];
         }
+    }
+}
+
+// ---- middle stage (3-stage transforms): digit i1, in place ------------------------------------
+template <class S, class Acc> HD void dif_stage_mid(int j, float2* v, const float2* tw, const Acc& acc)
+{
+    constexpr int R = S::R1, NB = (S::L / R) / S::NTS;
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        const int jb = j + S::NTS * b;
+        const int k0 = jb / S::R2, i2 = jb % S::R2;
+        float2* vb = v + b * R;
+        float2* p = acc.at(k0, i2);
+#pragma unroll
+        for (int m = 0; m < R; m++) vb[m] = p[m * S::R2 * Acc::unit()];
+        Bfly<R>::run(vb);
+        const float2* tb = tw + S::OFF_B1 + i2;
+        apply_powers<R>(vb, [&](int row) { return tb[row * S::R2]; });
+#pragma unroll
+        for (int m = 0; m < R; m++) p[m * S::R2 * Acc::unit()] = vb[m];
+    }
+}
+
+// ---- last stage (NSTAGE >= 2): digit i_last (stride 1); results stay in registers ---------------
+template <class S, class Acc> HD void dif_stage_last(int j, float2* v, const Acc& acc)
+{
+    constexpr int R = S::RLAST, NB = (S::L / R) / S::NTS;
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        const int jb = j + S::NTS * b;
+        float2* vb = v + b * R;
+        const float2* p = acc.at(jb % S::R0, (jb / S::R0) * R);
+#pragma unroll
+        for (int m = 0; m < R; m++) vb[m] = p[m * Acc::unit()];
         Bfly<R>::run(vb);
     }
 }
 
-// One stage, second half: scatter the butterfly outputs through `dst(index, value)`.
-template <class S, int STAGE, class Dst> HD void stage_scatter(int j, const float2* v, Dst dst)
-{
-    typedef StageInfo<S, STAGE> I;
-    constexpr int R = I::R, NS = I::NS;
-    constexpr int NBF = S::L / R;
-    constexpr int NB = NBF / S::NTS;
-#pragma unroll
-    for (int b = 0; b < NB; b++) {
-        const int jb = j + S::NTS * b;
-        const int base = (jb / NS) * NS * R + (jb % NS);
-#pragma unroll
-        for (int m = 0; m < R; m++) dst(base + m * NS, v[b * R + m]);
-    }
-}
-
-// For the LAST stage the output index is jb + m*NSLAST; this visits (out_index, value, b, m).
+// Visit the outputs of the last stage: (output index jb + m*NSLAST, value, b, m).
 template <class S, class Dst> HD void last_stage_visit(int j, const float2* v, Dst dst)
 {
     constexpr int R = S::RLAST;

@@ -9,6 +9,9 @@
 //   path the per-column factor exp(-j2pi df n2/fs) commutes with the column DFT and is folded into it).
 // Inverse (COL_INV_*): B[k1][n2] -> z[n1*N2 + n2], either reduced to the first-max of |z|^2 with index
 //   p = nq*(n1*N2+n2) + q (polyphase q of the x3 interpolated correlation) or stored.
+//
+// Work items (column tile, matrix) are walked by whatever grid is launched (one CTA per item or a
+// resident wave looping over items), like the row pass.
 #pragma once
 #include "fft_core.cuh"
 
@@ -23,9 +26,13 @@ struct ColParams {
     const float2* blob;
     i64 N;                 // L * N2
     int N2;
+    double invN;           // 1/N
+    int ntx;               // column tiles per matrix
+    int ny;                // matrices in this launch: records (SRC_RAW), lanes (CF32 fwd), lanes*nq (inverse)
     // SRC_RAW
     int nch;               // channels interleaved per sample instant (2: [I1 Q1 I2 Q2], 1: [I Q])
-    int op;                // 0 none, 1 derotate, 2 square, 4 fourth power
+    // (the pre-transform operation is the kernel's OP template parameter:
+    //  0 none, 1 derotate, 2 square, 4 fourth power)
     int sub_mean;
     const double* sums;    // [lane][2] sum(I), sum(Q) over the window (exact integers)
     const float2* lrow;    // [lane][L]  exp(-j2pi df N2 n1/fs)
@@ -38,29 +45,30 @@ struct ColParams {
     float2 code_mean;
     // COL_INV_*
     int nq;
-    u64* part_key;         // [blk.y][ntile]
-    int ntile;             // gridDim.x
+    u64* part_key;         // [y][ntx]
 };
 
-template <class S, int TS, int SRC, int MODE> struct KCol {
+template <class S, int TS, int SRC, int MODE, int OP = 0> struct KCol {
     typedef ColParams Params;
     static const char* name()
     {
         return MODE == COL_INV_ARGMAX ? "col_inv_argmax" : MODE == COL_INV_STORE ? "col_inv_store"
              : SRC == SRC_RAW ? "col_fwd_raw" : SRC == SRC_BITS ? "col_fwd_bits" : "col_fwd_cf32";
     }
+    static constexpr bool PERSISTENT = true;
     static constexpr int NTA = S::NTS * TS;
     static constexpr int NT = (NTA + 31) / 32 * 32;
     static constexpr int MINB = (S::L * TS >= 8000) ? 2 : 4;
+    typedef ColAcc<S::SP0, TS> Acc;
     static constexpr int NG = (MODE == COL_FWD) ? TS * S::RLAST : 0;
     static constexpr int OFF_G = S::BLOB_PAD;
     static constexpr int OFF_DATA = OFF_G + ((NG + 1) & ~1);
-    static constexpr int NCOMP = S::NSTAGE == 3 ? 4 : 2;   // single-stage: phase 0 = tables only
-    static constexpr int P_S0 = S::NSTAGE == 1 ? 1 : 0;       // phase that runs stage 0
+    static constexpr int NCOMP = S::NSTAGE == 1 ? 2 : S::NSTAGE;
     static constexpr bool HASFIN = (MODE == COL_INV_ARGMAX);
     static constexpr int NPH = NCOMP + (HASFIN ? 1 : 0);
     static constexpr int NSUM = 1;
     static constexpr int NBL = (S::L / S::RLAST) / S::NTS;
+    static constexpr int NB0 = S::SP0 / S::NTS;
     struct Regs {
         float2 v[S::E];
         u64 key;
@@ -74,67 +82,122 @@ template <class S, int TS, int SRC, int MODE> struct KCol {
     {
         return (ph == NCOMP - 1 && MODE == COL_INV_ARGMAX) ? SYNC_MAXKEY : SYNC_BARRIER;
     }
-
-    // ---- element fetch for stage 0 (n1 = idx) ------------------------------------------------
-    static HD float2 fetch(const Params& p, const Blk& blk, int col, int idx, float mx, float my, i64 lane)
+    static HD int niter(const Params& p, int bx, int gdim)
     {
+        const i64 total = (i64)p.ntx * p.ny;
+        return bx < total ? (int)((total - bx + gdim - 1) / gdim) : 0;
+    }
+    struct Work { int x, y; };
+    static HD Work work_of(const Params& p, const Blk& blk, int it)
+    {
+        const i64 w = (i64)blk.x + (i64)it * blk.gx;
+        Work k;
+        k.x = (int)(w % p.ntx);
+        k.y = (int)(w / p.ntx);
+        return k;
+    }
+
+    static HD float2 pre_op(float2 x, float2 lr)
+    {
+        if (OP == 1) x = cmul(x, lr);
+        else if (OP >= 2) {
+            x = make_float2(x.x * x.x - x.y * x.y, 2.f * x.x * x.y);
+            if (OP == 4) x = make_float2(x.x * x.x - x.y * x.y, 2.f * x.x * x.y);
+        }
+        return x;
+    }
+
+    // stage-0 operands straight from global memory (rows j + NTS*b + m*SP0 of column `col`),
+    // with the int16 unpack / mean removal / pre-transform operation fused in
+    static HD void load0(const Params& p, const Work& wk, int s, int j, Regs& r)
+    {
+        const int col = wk.x * TS + s;
         if (SRC == SRC_RAW) {
-            const i64 rowlen = (i64)p.nch * p.N2;
-            const i64 base = p.rec_offset ? p.rec_offset[blk.y] : (i64)blk.y * p.rec_stride;
-            const short2 raw = reinterpret_cast<const short2*>(p.src)[base + (i64)idx * rowlen + col];
-            float2 x = make_float2((float)raw.x - mx, (float)raw.y - my);
-            if (p.op == 1) x = cmul(x, p.lrow[lane * S::L + idx]);
-            else if (p.op >= 2) {
-                x = make_float2(x.x * x.x - x.y * x.y, 2.f * x.x * x.y);
-                if (p.op == 4) x = make_float2(x.x * x.x - x.y * x.y, 2.f * x.x * x.y);
+            const i64 lane = (i64)wk.y * p.nch + col % p.nch;
+            float mx = 0.f, my = 0.f;
+            if (p.sub_mean) {
+                mx = (float)(p.sums[lane * 2] * p.invN);
+                my = (float)(p.sums[lane * 2 + 1] * p.invN);
             }
-            return x;
+            const i64 rowlen = (i64)p.nch * p.N2;
+            const i64 rbase = p.rec_offset ? p.rec_offset[wk.y] : (i64)wk.y * p.rec_stride;
+            const short2* gsrc = reinterpret_cast<const short2*>(p.src) + rbase + (i64)j * rowlen + col;
+            const i64 bstride = (i64)S::NTS * rowlen, mstride = (i64)S::SP0 * rowlen;
+            const float2* lr = p.lrow + lane * S::L + j;
+#pragma unroll
+            for (int b = 0; b < NB0; b++)
+#pragma unroll
+                for (int m = 0; m < S::R0; m++) {
+                    const short2 raw = gsrc[b * bstride + m * mstride];
+                    const float2 x = make_float2((float)raw.x - mx, (float)raw.y - my);
+                    r.v[b * S::R0 + m] = pre_op(x, OP == 1 ? lr[S::NTS * b + m * S::SP0] : x);
+                }
         } else if (SRC == SRC_CF32) {
-            const float2 x = reinterpret_cast<const float2*>(p.src)[(i64)blk.y * p.N + (i64)idx * p.N2 + col];
-            return (MODE == COL_FWD) ? x : cswap(x);
-        } else {  // SRC_BITS: sample n = idx*N2 + col holds chip n/rep
-            const i64 n = (i64)idx * p.N2 + col;
-            const i64 chip = n / p.rep;
+            const float2* gsrc = reinterpret_cast<const float2*>(p.src) + (i64)wk.y * p.N + (i64)j * p.N2 + col;
+            const i64 bstride = (i64)S::NTS * p.N2, mstride = (i64)S::SP0 * p.N2;
+#pragma unroll
+            for (int b = 0; b < NB0; b++)
+#pragma unroll
+                for (int m = 0; m < S::R0; m++) {
+                    const float2 x = gsrc[b * bstride + m * mstride];
+                    r.v[b * S::R0 + m] = (MODE == COL_FWD) ? x : cswap(x);
+                }
+        } else {  // SRC_BITS: sample n = n1*N2 + col holds chip n/rep
             const unsigned char* bits = reinterpret_cast<const unsigned char*>(p.src);
-            if (p.qpsk) return make_float2((float)bits[2 * chip] - p.code_mean.x, (float)bits[2 * chip + 1] - p.code_mean.y);
-            return make_float2(2.f * (float)bits[chip] - 1.f, 0.f);
+#pragma unroll
+            for (int b = 0; b < NB0; b++)
+#pragma unroll
+                for (int m = 0; m < S::R0; m++) {
+                    const i64 n = (i64)(j + S::NTS * b + m * S::SP0) * p.N2 + col;
+                    const i64 chip = n / p.rep;
+                    r.v[b * S::R0 + m] = p.qpsk ? make_float2((float)bits[2 * chip] - p.code_mean.x,
+                                                              (float)bits[2 * chip + 1] - p.code_mean.y)
+                                                : make_float2(2.f * (float)bits[chip] - 1.f, 0.f);
+                }
         }
     }
 
-    static HD void epilogue(const Params& p, const Blk& blk, int s, int j, int col, Regs& r, const float2* sm)
+    static HD void epilogue(const Params& p, const Work& wk, int s, int j, Regs& r, const float2* g)
     {
+        const int col = wk.x * TS + s;
         const int ch = (SRC == SRC_RAW) ? col % p.nch : 0;
         const int n2 = (SRC == SRC_RAW) ? col / p.nch : col;
         if (MODE == COL_FWD) {
-            const i64 lane = (SRC == SRC_RAW) ? (i64)blk.y * p.nch + ch : (i64)blk.y;
+            const i64 lane = (SRC == SRC_RAW) ? (i64)wk.y * p.nch + ch : (i64)wk.y;
             float2* d = p.dst + lane * p.N + n2;
-            const float2* g = sm + OFF_G;
             float2 base[NBL];
 #pragma unroll
             for (int b = 0; b < NBL; b++) {
                 const int jb = j + S::NTS * b;
-                base[b] = cis_cycles(-(double)((i64)n2 * jb) / (double)p.N);
-                if (SRC == SRC_RAW && p.op == 1) base[b] = cmul(base[b], p.lcol[lane * p.N2 + n2]);
+                base[b] = cis_cycles(-(double)((i64)n2 * jb) * p.invN);
+                if (SRC == SRC_RAW && OP == 1) base[b] = cmul(base[b], p.lcol[lane * p.N2 + n2]);
             }
-            last_stage_visit<S>(j, r.v, [&](int o, float2 x, int b, int m) {
-                d[(i64)o * p.N2] = cmul(x, cmul(base[b], g[m * TS + s]));
+            const i64 bstr = (i64)S::NTS * p.N2, mstr = (i64)S::NSLAST * p.N2;
+            float2* dj = d + (i64)j * p.N2;
+            last_stage_visit<S>(j, r.v, [&](int, float2 x, int b, int m) {
+                dj[b * bstr + m * mstr] = cmul(x, cmul(base[b], g[m * TS + s]));
             });
         } else if (MODE == COL_INV_STORE) {
-            float2* d = p.dst + (i64)blk.y * p.N + n2;
-            last_stage_visit<S>(j, r.v, [&](int o, float2 x, int, int) { d[(i64)o * p.N2] = cswap(x); });
-        } else {  // COL_INV_ARGMAX
-            const int q = blk.y % p.nq;
-            u64 best = 0;
+            float2* dj = p.dst + (i64)wk.y * p.N + n2 + (i64)j * p.N2;
+            const i64 bstr = (i64)S::NTS * p.N2, mstr = (i64)S::NSLAST * p.N2;
+            last_stage_visit<S>(j, r.v, [&](int, float2 x, int b, int m) { dj[b * bstr + m * mstr] = cswap(x); });
+        } else {  // COL_INV_ARGMAX: outputs are visited in increasing index, so '>' keeps the first maximum
+            const int q = wk.y % p.nq;
+            float bestv = -1.f;
+            unsigned besti = 0;
+            const unsigned i0 = (unsigned)p.nq * (unsigned)n2 + (unsigned)q;
+            const unsigned istep = (unsigned)p.nq * (unsigned)p.N2;
             last_stage_visit<S>(j, r.v, [&](int o, float2 x, int, int) {
-                const i64 pidx = (i64)p.nq * ((i64)o * p.N2 + n2) + q;
-                u64 k = make_key(cnorm(x), (unsigned)pidx);
-                best = k > best ? k : best;
+                const float v = cnorm(x);
+                const unsigned idx = i0 + istep * (unsigned)o;
+                if (v > bestv || (NBL > 1 && v == bestv && idx < besti)) { bestv = v; besti = idx; }
             });
-            r.key = best;
+            r.key = make_key(bestv, besti);
         }
     }
 
-    template <int PH> static HD void phase(const Params& p, const Blk& blk, int tid, Regs& r, unsigned char* smem)
+    template <int PH>
+    static HD void phase(const Params& p, const Blk& blk, int tid, Regs& r, unsigned char* smem, int it, int nit)
     {
         float2* sm = reinterpret_cast<float2*>(smem);
         if (tid >= NTA) {
@@ -143,49 +206,36 @@ template <class S, int TS, int SRC, int MODE> struct KCol {
             return;
         }
         const int s = tid % TS, j = tid / TS;
-        const int col = blk.x * TS + s;
-        float2* data = sm + OFF_DATA;
-        auto sm_src = [&](int i) { return data[i * TS + s]; };
-        auto sm_dst = [&](int i, float2 x) { data[i * TS + s] = x; };
+        const Acc acc{sm + OFF_DATA + s};
+        const Work wk = work_of(p, blk, it);
+        float2* gtab = sm + OFF_G;
+
         if (PH == 0) {
             r.key = 0;
             r.dsum[0] = 0.0;
-            for (int i = tid; i < S::BLOB; i += NTA) sm[i] = p.blob[i];
+            if (it == 0 && S::NSTAGE == 3)          // only the middle stage reads the shared copy
+                for (int i = tid; i < S::BLOB; i += NTA) sm[i] = p.blob[i];
             if (MODE == COL_FWD) {
                 for (int t = tid; t < NG; t += NTA) {
                     const int s2 = t % TS, m = t / TS;
-                    const int col2 = blk.x * TS + s2;
+                    const int col2 = wk.x * TS + s2;
                     const i64 n2b = (SRC == SRC_RAW) ? col2 / p.nch : col2;
-                    sm[OFF_G + m * TS + s2] = cis_cycles(-(double)(n2b * S::NSLAST * m) / (double)p.N);
+                    gtab[m * TS + s2] = cis_cycles(-(double)(n2b * S::NSLAST * m) * p.invN);
                 }
             }
         }
-        if (PH == P_S0) {
-            float mx = 0.f, my = 0.f;
-            i64 lane = 0;
-            if (SRC == SRC_RAW) {
-                lane = (i64)blk.y * p.nch + col % p.nch;
-                if (p.sub_mean) {
-                    const double invn = 1.0 / (double)p.N;
-                    mx = (float)(p.sums[lane * 2] * invn);
-                    my = (float)(p.sums[lane * 2 + 1] * invn);
-                }
-            }
-            stage_compute<S, 0>(j, r.v, sm, [&](int i) { return fetch(p, blk, col, i, mx, my, lane); });
-            if (S::NSTAGE == 1) epilogue(p, blk, s, j, col, r, sm);
-            else stage_scatter<S, 0>(j, r.v, sm_dst);
+        if (PH == (S::NSTAGE == 1 ? 1 : 0)) {
+            load0(p, wk, s, j, r);
+            dif_stage0<S>(j, r.v, p.blob, acc);      // stage-0 seeds from global/L1 (shared copy not yet valid)
+            if (S::NSTAGE == 1) epilogue(p, wk, s, j, r, gtab);
         }
-        if (S::NSTAGE >= 2 && PH == 1) {
-            stage_compute<S, 1>(j, r.v, sm, sm_src);
-            if (S::NSTAGE == 2) epilogue(p, blk, s, j, col, r, sm);
-        }
-        if (S::NSTAGE == 3 && PH == 2) stage_scatter<S, 1>(j, r.v, sm_dst);
-        if (S::NSTAGE == 3 && PH == 3) {
-            stage_compute<S, 2>(j, r.v, sm, sm_src);
-            epilogue(p, blk, s, j, col, r, sm);
+        if (S::NSTAGE == 3 && PH == 1) dif_stage_mid<S>(j, r.v, sm, acc);
+        if (S::NSTAGE >= 2 && PH == S::NSTAGE - 1) {
+            dif_stage_last<S>(j, r.v, acc);
+            epilogue(p, wk, s, j, r, gtab);
         }
         if (HASFIN && PH == NCOMP) {
-            if (tid == 0) p.part_key[(i64)blk.y * p.ntile + blk.x] = r.key;
+            if (tid == 0) p.part_key[(i64)wk.y * p.ntx + wk.x] = r.key;
         }
     }
 };

@@ -7,6 +7,9 @@
 // over n2 -> k2 and position (k1,k2) holds bin k = k1 + N1*k2 ("transposed" spectrum order, never
 // un-transposed: the code spectrum, the pad/twist tables and the windows use the same order).
 //
+// Work items (row group, lane[, polyphase q]) are walked by whatever grid is launched: one CTA per
+// item, or a resident wave of CTAs looping over items (the launcher inserts a barrier between items).
+//
 // MODES
 //   ROW_FWD_STORE   plain store                               (code spectrum C = fft(code))
 //   ROW_FWD_ARGMAX  |X|^2 first-max inside a window of the fftshift'ed axis (carrier estimator A3)
@@ -26,18 +29,21 @@ struct RowParams {
     const float2* blob;      // S::BLOB twiddle entries
     i64 N;                   // N1 * L
     int N1;
+    double invN, invM;       // 1/N, 1/(nq*N)
+    int nlanes;              // lanes in this launch
+    int nblk;                // row groups per lane (N1 / RPC)
     // ROW_FWD_ARGMAX
     i64 win_lo, win_hi;      // inclusive window, index s of fftshift(X): s = (k + N/2) mod N
-    u64* part_key;           // [lane][gridDim.x]
+    u64* part_key;           // [lane][nblk]
+    int oa1, ob1, oa2, ob2;  // k2 ranges that can intersect the window (superset; exact test follows)
     // ROW_FWD_MULCODE
     const float2* code;      // C in the transposed order [k1][k2]
     int conj_mode;           // 0: Y*conj(C) (variant G)   1: conj(Y)*C (variant K)
-    double* part_energy;     // [lane][gridDim.x]  sum |Y|^2
+    double* part_energy;     // [lane][nblk]  sum |Y|^2
     float2* y0;              // [lane] Y[0]
     // ROW_INV_TWIST
     const float2* twq;       // [nq][L] per-k2 twist (includes the negative-side factor), row 0 unused
     int nq;                  // 3 (x3 interpolation) or 1
-    int nblk;                // gridDim.x (for partial indexing)
 };
 
 template <class S, int RPC, int MODE> struct KRow {
@@ -47,19 +53,21 @@ template <class S, int RPC, int MODE> struct KRow {
         return MODE == ROW_FWD_STORE ? "row_fwd_store" : MODE == ROW_FWD_ARGMAX ? "row_fwd_argmax"
              : MODE == ROW_FWD_MULCODE ? "row_fwd_mulcode" : "row_inv_twist";
     }
+    static constexpr bool PERSISTENT = true;
     static constexpr int NTA = S::NTS * RPC;
     static constexpr int NT = (NTA + 31) / 32 * 32;
     static constexpr int MINB = (S::L * RPC >= 8000) ? 2 : 4;
-    static constexpr int ROWSM = S::L + S::L / S::R0 + 2;      // padded row (float2 units)
+    typedef RowAcc<S::SP0> Acc;
+    static constexpr int ROWSM = (S::R0 * Acc::BSTRIDE + 1) & ~1;      // padded row (float2 units)
     static constexpr int NG = (MODE == ROW_INV_TWIST) ? RPC * S::RLAST : 0;
     static constexpr int OFF_G = S::BLOB_PAD;
     static constexpr int OFF_DATA = OFF_G + ((NG + 1) & ~1);
-    static constexpr int NCOMP = S::NSTAGE == 3 ? 4 : 2;   // single-stage: phase 0 = tables only
-    static constexpr int P_S0 = S::NSTAGE == 1 ? 1 : 0;       // phase that runs stage 0
+    static constexpr int NCOMP = S::NSTAGE == 1 ? 2 : S::NSTAGE;       // 1-stage: phase 0 = tables only
     static constexpr bool HASFIN = (MODE == ROW_FWD_ARGMAX || MODE == ROW_FWD_MULCODE);
     static constexpr int NPH = NCOMP + (HASFIN ? 1 : 0);
     static constexpr int NSUM = 1;
     static constexpr int NBL = (S::L / S::RLAST) / S::NTS;     // butterflies per thread in the last stage
+    static constexpr int NB0 = S::SP0 / S::NTS;                // stage-0 butterflies per thread
     struct Regs {
         float2 v[S::E];
         u64 key;
@@ -74,25 +82,92 @@ template <class S, int RPC, int MODE> struct KRow {
         return (ph == NCOMP - 1) ? (MODE == ROW_FWD_ARGMAX ? SYNC_MAXKEY : (MODE == ROW_FWD_MULCODE ? SYNC_SUMD : SYNC_BARRIER))
                                  : SYNC_BARRIER;
     }
-    static HD int pad(int i) { return i + i / S::R0; }
-
-    static HD void epilogue(const Params& p, const Blk& blk, int rl, int j, Regs& r, const float2* sm)
+    // work decomposition: item w -> (x = w % gx, lane = w / gx); for ROW_INV_TWIST x = rowblk*nq + q
+    // (q fastest, so the CTAs that re-read the same rows of P run together and hit in L2)
+    static HD int gx(const Params& p) { return p.nblk * (MODE == ROW_INV_TWIST ? p.nq : 1); }
+    static HD i64 total_work(const Params& p) { return (i64)gx(p) * p.nlanes; }
+    static HD int niter(const Params& p, int bx, int gdim)
     {
-        const int row = blk.x * RPC + rl;
-        const i64 lane = blk.y;
+        const i64 total = total_work(p);
+        return bx < total ? (int)((total - bx + gdim - 1) / gdim) : 0;
+    }
+    struct Work { int rowblk, q; i64 lane; };
+    static HD Work work_of(const Params& p, const Blk& blk, int it)
+    {
+        const i64 w = (i64)blk.x + (i64)it * blk.gx;
+        const int g = gx(p);
+        const int x = (int)(w % g);
+        Work k;
+        k.lane = w / g;
+        k.rowblk = MODE == ROW_INV_TWIST ? x / p.nq : x;
+        k.q = MODE == ROW_INV_TWIST ? x % p.nq : 0;
+        return k;
+    }
+
+    // bits m (0..RLAST-1) for which the output index jb + m*NSLAST lies in [oa, ob]
+    static HD unsigned slot_mask(int oa, int ob, int jb)
+    {
+        if (ob < oa) return 0u;
+        const int lo = oa - jb, hi = ob - jb;
+        if (hi < 0) return 0u;
+        const int mlo = lo <= 0 ? 0 : (lo + S::NSLAST - 1) / S::NSLAST;
+        int mhi = hi / S::NSLAST;
+        if (mhi > S::RLAST - 1) mhi = S::RLAST - 1;
+        if (mlo > mhi) return 0u;
+        return ((2u << mhi) - 1u) & ~((1u << mlo) - 1u);
+    }
+
+    // stage-0 operands straight from global memory: element jb + m*SP0 of this thread's row
+    static HD void load0(const Params& p, const Work& wk, int rl, int j, Regs& r)
+    {
+        const float2* xj = p.src + wk.lane * p.N + (i64)(wk.rowblk * RPC + rl) * S::L + j;
+        if (MODE == ROW_INV_TWIST) {
+            const int q = wk.q;
+            const float2* tj = p.twq + (i64)q * S::L + j;
+#pragma unroll
+            for (int b = 0; b < NB0; b++)
+#pragma unroll
+                for (int m = 0; m < S::R0; m++) {
+                    float2 z = xj[S::NTS * b + m * S::SP0];
+                    if (q > 0) z = cmul(z, tj[S::NTS * b + m * S::SP0]);
+                    r.v[b * S::R0 + m] = cswap(z);
+                }
+        } else {
+#pragma unroll
+            for (int b = 0; b < NB0; b++)
+#pragma unroll
+                for (int m = 0; m < S::R0; m++) r.v[b * S::R0 + m] = xj[S::NTS * b + m * S::SP0];
+        }
+    }
+
+    static HD void epilogue(const Params& p, const Work& wk, int rl, int j, Regs& r, const float2* g)
+    {
+        const int row = wk.rowblk * RPC + rl;
+        const i64 lane = wk.lane;
         const i64 rowoff = (i64)row * S::L;
         if (MODE == ROW_FWD_STORE) {
             float2* d = p.dst + lane * p.N + rowoff;
             last_stage_visit<S>(j, r.v, [&](int o, float2 x, int, int) { d[o] = x; });
         } else if (MODE == ROW_FWD_ARGMAX) {
+            // Cheap reject first: only k2 in [oa1,ob1] u [oa2,ob2] (host-computed superset) can fall in
+            // the window; turn that into a per-thread bit mask over the output slots m, then run the
+            // exact test on the fftshift'ed index s for those few only.
             u64 best = 0;
             const i64 half = p.N / 2;
-            last_stage_visit<S>(j, r.v, [&](int o, float2 x, int, int) {
-                i64 s = (i64)row + (i64)p.N1 * o + half;
-                if (s >= p.N) s -= p.N;
-                if (s >= p.win_lo && s <= p.win_hi) {
-                    u64 k = make_key(cnorm(x), (unsigned)s);
-                    best = k > best ? k : best;
+            unsigned mask[NBL];
+#pragma unroll
+            for (int b = 0; b < NBL; b++) {
+                const int jb = j + S::NTS * b;
+                mask[b] = slot_mask(p.oa1, p.ob1, jb) | slot_mask(p.oa2, p.ob2, jb);
+            }
+            last_stage_visit<S>(j, r.v, [&](int o, float2 x, int b, int m) {
+                if (mask[b] & (1u << m)) {
+                    i64 s = (i64)row + (i64)p.N1 * o + half;
+                    if (s >= p.N) s -= p.N;
+                    if (s >= p.win_lo && s <= p.win_hi) {
+                        u64 k = make_key(cnorm(x), (unsigned)s);
+                        best = k > best ? k : best;
+                    }
                 }
             });
             r.key = best;
@@ -105,27 +180,27 @@ template <class S, int RPC, int MODE> struct KRow {
                 float2 cc = c[o];
                 e += cnorm(x);
                 d[o] = cm ? cmul(cconj(x), cc) : cmulc(x, cc);
-                if (row == 0 && o == 0) p.y0[lane] = x;
             });
+            if (row == 0 && j == 0) p.y0[lane] = r.v[0];
             r.dsum[0] = (double)e;
         } else {  // ROW_INV_TWIST
-            const int q = blk.z;
+            const int q = wk.q;
             float2* d = p.dst + (lane * p.nq + q) * p.N + rowoff;
-            const float2* g = sm + OFF_G + rl * S::RLAST;
+            const float2* gr = g + rl * S::RLAST;
             float2 base[NBL];
 #pragma unroll
             for (int b = 0; b < NBL; b++) {
                 const int jb = j + S::NTS * b;
-                base[b] = cis_cycles((double)((i64)row * jb) / (double)p.N +
-                                     (double)((i64)q * row) / ((double)p.nq * (double)p.N));
+                base[b] = cis_cycles((double)((i64)row * jb) * p.invN + (double)((i64)q * row) * p.invM);
             }
             last_stage_visit<S>(j, r.v, [&](int o, float2 x, int b, int m) {
-                d[o] = cmul(cswap(x), cmul(base[b], g[m]));
+                d[o] = cmul(cswap(x), cmul(base[b], gr[m]));
             });
         }
     }
 
-    template <int PH> static HD void phase(const Params& p, const Blk& blk, int tid, Regs& r, unsigned char* smem)
+    template <int PH>
+    static HD void phase(const Params& p, const Blk& blk, int tid, Regs& r, unsigned char* smem, int it, int nit)
     {
         float2* sm = reinterpret_cast<float2*>(smem);
         if (tid >= NTA) {
@@ -134,52 +209,38 @@ template <class S, int RPC, int MODE> struct KRow {
             return;
         }
         const int rl = tid / S::NTS, j = tid % S::NTS;
-        const int row = blk.x * RPC + rl;
-        const i64 lane = blk.y;
-        float2* data = sm + OFF_DATA + rl * ROWSM;
-        auto sm_src = [&](int i) { return data[pad(i)]; };
-        auto sm_dst = [&](int i, float2 x) { data[pad(i)] = x; };
+        const Acc acc{sm + OFF_DATA + rl * ROWSM};
+        const Work wk = work_of(p, blk, it);
+        float2* gtab = sm + OFF_G;
+
         if (PH == 0) {
             r.key = 0;
             r.dsum[0] = 0.0;
-            for (int i = tid; i < S::BLOB; i += NTA) sm[i] = p.blob[i];
+            if (it == 0 && S::NSTAGE == 3)          // only the middle stage reads the shared copy
+                for (int i = tid; i < S::BLOB; i += NTA) sm[i] = p.blob[i];
             if (MODE == ROW_INV_TWIST) {
                 for (int t = tid; t < NG; t += NTA) {
                     const int rl2 = t / S::RLAST, m = t % S::RLAST;
-                    const i64 row2 = (i64)blk.x * RPC + rl2;
-                    sm[OFF_G + t] = cis_cycles((double)(row2 * S::NSLAST * m) / (double)p.N);
+                    const i64 row2 = (i64)wk.rowblk * RPC + rl2;
+                    gtab[t] = cis_cycles((double)(row2 * S::NSLAST * m) * p.invN);
                 }
             }
         }
-        if (PH == P_S0) {
-            const float2* s = p.src + lane * p.N + (i64)row * S::L;
-            if (MODE == ROW_INV_TWIST) {
-                const int q = blk.z;
-                const float2* tq = p.twq + (i64)q * S::L;
-                stage_compute<S, 0>(j, r.v, sm, [&](int i) {
-                    float2 z = s[i];
-                    if (q > 0) z = cmul(z, tq[i]);
-                    return cswap(z);
-                });
-            } else {
-                stage_compute<S, 0>(j, r.v, sm, [&](int i) { return s[i]; });
-            }
-            if (S::NSTAGE == 1) epilogue(p, blk, rl, j, r, sm);
-            else stage_scatter<S, 0>(j, r.v, sm_dst);
+        if (PH == (S::NSTAGE == 1 ? 1 : 0)) {
+            load0(p, wk, rl, j, r);
+            dif_stage0<S>(j, r.v, p.blob, acc);      // stage-0 seeds straight from global/L1: the shared copy
+                                                     // of the blob is only valid after the first barrier
+            if (S::NSTAGE == 1) epilogue(p, wk, rl, j, r, gtab);
         }
-        if (S::NSTAGE >= 2 && PH == 1) {
-            stage_compute<S, 1>(j, r.v, sm, sm_src);
-            if (S::NSTAGE == 2) epilogue(p, blk, rl, j, r, sm);
-        }
-        if (S::NSTAGE == 3 && PH == 2) stage_scatter<S, 1>(j, r.v, sm_dst);
-        if (S::NSTAGE == 3 && PH == 3) {
-            stage_compute<S, 2>(j, r.v, sm, sm_src);
-            epilogue(p, blk, rl, j, r, sm);
+        if (S::NSTAGE == 3 && PH == 1) dif_stage_mid<S>(j, r.v, sm, acc);
+        if (S::NSTAGE >= 2 && PH == S::NSTAGE - 1) {
+            dif_stage_last<S>(j, r.v, acc);
+            epilogue(p, wk, rl, j, r, gtab);
         }
         if (HASFIN && PH == NCOMP) {
             if (tid == 0) {
-                if (MODE == ROW_FWD_ARGMAX) p.part_key[lane * p.nblk + blk.x] = r.key;
-                if (MODE == ROW_FWD_MULCODE) p.part_energy[lane * p.nblk + blk.x] = r.dsum[0];
+                if (MODE == ROW_FWD_ARGMAX) p.part_key[wk.lane * p.nblk + wk.rowblk] = r.key;
+                if (MODE == ROW_FWD_MULCODE) p.part_energy[wk.lane * p.nblk + wk.rowblk] = r.dsum[0];
             }
         }
     }

@@ -49,6 +49,7 @@ struct MeanParams {
 struct KMean {
     typedef MeanParams Params;
     static const char* name() { return "mean"; }
+    static constexpr bool PERSISTENT = false;
     static constexpr int NT = 256, MINB = 4, NPH = 2, NSUM = 4;
     struct Regs { u64 key; double dsum[NSUM]; };
     static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }
@@ -59,19 +60,37 @@ struct KMean {
             const i64 base = p.rec_offset ? p.rec_offset[blk.y] : (i64)blk.y * p.rec_stride;
             const short2* s = p.src + base;
             const i64 stride = (i64)p.nblk * NT;      // even, so a thread always sees the same channel
-            i64 sx = 0, sy = 0;
             const i64 e0 = (i64)blk.x * NT + tid;
+            i64 a0x = 0, a0y = 0, a1x = 0, a1y = 0;   // channel 0 / channel 1 (nch == 2) accumulators
+            if ((base & 3) == 0 && (p.nelem & 3) == 0 && ((size_t)p.src & 15) == 0) {
+                // 16-byte loads: 4 complex-int16 elements = [ch0 ch1 ch0 ch1] (nch 2) or 4 x ch0 (nch 1)
+                const int4* s4 = reinterpret_cast<const int4*>(s);
+                const i64 nquad = p.nelem >> 2;
+                int q0x = 0, q0y = 0, q1x = 0, q1y = 0;
 #pragma unroll 4
-            for (i64 e = e0; e < p.nelem; e += stride) {
-                const short2 v = s[e];
-                sx += v.x;
-                sy += v.y;
+                for (i64 e = e0; e < nquad; e += stride) {
+                    const int4 v = s4[e];
+                    q0x += (int)(short)(v.x & 0xffff) + (int)(short)(v.z & 0xffff);
+                    q0y += (v.x >> 16) + (v.z >> 16);
+                    q1x += (int)(short)(v.y & 0xffff) + (int)(short)(v.w & 0xffff);
+                    q1y += (v.y >> 16) + (v.w >> 16);
+                }
+                if (p.nch == 2) { a0x = q0x; a0y = q0y; a1x = q1x; a1y = q1y; }
+                else { a0x = (i64)q0x + q1x; a0y = (i64)q0y + q1y; }
+            } else {
+                i64 sx = 0, sy = 0;
+#pragma unroll 4
+                for (i64 e = e0; e < p.nelem; e += stride) {
+                    const short2 v = s[e];
+                    sx += v.x;
+                    sy += v.y;
+                }
+                if ((int)(e0 % p.nch) == 0) { a0x = sx; a0y = sy; } else { a1x = sx; a1y = sy; }
             }
-            const int ch = (int)(e0 % p.nch);
-            r.dsum[0] = ch == 0 ? (double)sx : 0.0;
-            r.dsum[1] = ch == 0 ? (double)sy : 0.0;
-            r.dsum[2] = ch == 1 ? (double)sx : 0.0;
-            r.dsum[3] = ch == 1 ? (double)sy : 0.0;
+            r.dsum[0] = (double)a0x;
+            r.dsum[1] = (double)a0y;
+            r.dsum[2] = (double)a1x;
+            r.dsum[3] = (double)a1y;
         } else if (tid == 0) {
             double* o = p.sums + (i64)blk.y * p.nch * 2;
             atomic_add_d(o + 0, r.dsum[0]);
@@ -107,6 +126,7 @@ struct DfParams {
 struct KDfFinal {
     typedef DfParams Params;
     static const char* name() { return "df_final"; }
+    static constexpr bool PERSISTENT = false;
     static constexpr int NT = 256, MINB = 4, NPH = 2, NSUM = 1;
     struct Regs { u64 key; double dsum[NSUM]; };
     static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }
@@ -168,6 +188,7 @@ struct PeakTabParams {
 struct KPeakTables {
     typedef PeakTabParams Params;
     static const char* name() { return "peak_tables"; }
+    static constexpr bool PERSISTENT = false;
     static constexpr int NT = 256, MINB = 4, NPH = 2, NSUM = 1;
     struct Regs { u64 key; double dsum[NSUM]; };
     static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }
@@ -222,6 +243,7 @@ template <int L1MAX> struct KPeakSums {
     typedef PeakSumParams Params;
     static const char* name() { return "peak_sums"; }
     static constexpr int KW = 16;                 // k2 columns per CTA
+    static constexpr bool PERSISTENT = false;
     static constexpr int NT = 256, MINB = 2, NPH = 3, NSUM = 2 * PEAK_NPTS;
     static constexpr int NGRP = NT / KW;
     struct Regs { u64 key; double dsum[NSUM]; };
@@ -241,14 +263,25 @@ template <int L1MAX> struct KPeakSums {
             float2 acc[PEAK_NPTS];
 #pragma unroll
             for (int d = 0; d < PEAK_NPTS; d++) acc[d] = make_float2(0.f, 0.f);
-#pragma unroll 4
-            for (int k1 = g; k1 < p.L1; k1 += NGRP) {
-                const float2 x = src[(i64)k1 * p.N2];
+            constexpr int BATCH = 10;     // loads in flight per thread
+            for (int k1b = g; k1b < p.L1; k1b += NGRP * BATCH) {
+                float2 x[BATCH];
 #pragma unroll
-                for (int d = 0; d < PEAK_NPTS; d++) {
-                    const float2 w = rp[d * p.L1 + k1];
-                    acc[d].x += x.x * w.x - x.y * w.y;
-                    acc[d].y += x.x * w.y + x.y * w.x;
+                for (int u = 0; u < BATCH; u++) {
+                    const int k1 = k1b + u * NGRP;
+                    x[u] = (k1 < p.L1) ? src[(i64)k1 * p.N2] : make_float2(0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < BATCH; u++) {
+                    const int k1 = k1b + u * NGRP;
+                    if (k1 < p.L1) {
+#pragma unroll
+                        for (int d = 0; d < PEAK_NPTS; d++) {
+                            const float2 w = rp[d * p.L1 + k1];
+                            acc[d].x += x[u].x * w.x - x[u].y * w.y;
+                            acc[d].y += x[u].x * w.y + x[u].y * w.x;
+                        }
+                    }
                 }
             }
 #pragma unroll
@@ -296,6 +329,7 @@ struct PeakFinParams {
 struct KPeakFinal {
     typedef PeakFinParams Params;
     static const char* name() { return "peak_final"; }
+    static constexpr bool PERSISTENT = false;
     static constexpr int NT = 256, MINB = 4, NPH = 2, NSUM = 2 * PEAK_NPTS + 1;
     struct Regs { u64 key; double dsum[NSUM]; };
     static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }
@@ -391,6 +425,7 @@ struct PrnParams {
 struct KPrnGen {
     typedef PrnParams Params;
     static const char* name() { return "prn_gen"; }
+    static constexpr bool PERSISTENT = false;
     static constexpr int NT = 128, MINB = 4, NPH = 1, NSUM = 1, CH = 64;
     struct Regs { u64 key; double dsum[NSUM]; };
     static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }

@@ -56,18 +56,21 @@ template <class K> __device__ __forceinline__ void block_sum_d(typename K::Regs&
     }
 }
 
+// Persistent kernels (K::PERSISTENT) loop over work items: phase<PH>(..., it, nit) is run for
+// it = 0..nit-1 with nit = K::niter(p, blockIdx.x, gridDim.x).
 template <class K, int PH>
 __device__ __forceinline__ void run_phases(const typename K::Params& p, const Blk& b, int tid,
-                                           typename K::Regs& r, unsigned char* smem)
+                                           typename K::Regs& r, unsigned char* smem, int it, int nit)
 {
-    K::template phase<PH>(p, b, tid, r, smem);
+    if constexpr (K::PERSISTENT) K::template phase<PH>(p, b, tid, r, smem, it, nit);
+    else K::template phase<PH>(p, b, tid, r, smem);
     if constexpr (PH + 1 < K::NPH) {
         constexpr int kind = K::sync_after(PH);
         unsigned char* scratch = smem + K::smem_bytes() - RED_SCRATCH_BYTES;
         if constexpr (kind == SYNC_BARRIER) __syncthreads();
         if constexpr (kind == SYNC_MAXKEY || kind == SYNC_MAXKEY_SUMD) block_max_key<K>(r, scratch);
         if constexpr (kind == SYNC_SUMD || kind == SYNC_MAXKEY_SUMD) block_sum_d<K>(r, scratch);
-        run_phases<K, PH + 1>(p, b, tid, r, smem);
+        run_phases<K, PH + 1>(p, b, tid, r, smem, it, nit);
     }
 }
 
@@ -75,8 +78,16 @@ template <class K> __global__ void __launch_bounds__(K::NT, K::MINB) kernel_entr
 {
     extern __shared__ __align__(16) unsigned char smem[];
     typename K::Regs r;
-    Blk b{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z};
-    run_phases<K, 0>(p, b, (int)threadIdx.x, r, smem);
+    Blk b{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z, (int)gridDim.x};
+    if constexpr (K::PERSISTENT) {
+        const int nit = K::niter(p, (int)blockIdx.x, (int)gridDim.x);
+        for (int it = 0; it < nit; it++) {
+            if (it > 0) __syncthreads();     // shared buffers of the previous item are free again
+            run_phases<K, 0>(p, b, (int)threadIdx.x, r, smem, it, nit);
+        }
+    } else {
+        run_phases<K, 0>(p, b, (int)threadIdx.x, r, smem, 0, 1);
+    }
 }
 
 // Device launcher: used by the product library.

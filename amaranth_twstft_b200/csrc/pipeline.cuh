@@ -10,6 +10,7 @@
 #pragma once
 #include <vector>
 #include <math.h>
+#include <stdlib.h>
 #include "backend.cuh"
 #include "k_row.cuh"
 #include "k_col.cuh"
@@ -89,9 +90,21 @@ public:
 
     template <class T> T* dalloc(size_t n) { return reinterpret_cast<T*>(be->alloc(n * sizeof(T))); }
 
+    // persistent kernels: one wave of resident CTAs, each looping over work items
+    bool persistent = false;   // false: one CTA per work item; true: one resident wave looping over items
+    template <class K> dim3 pgrid(i64 total) const
+    {
+        i64 g = persistent ? (i64)be->num_sms * K::MINB : total;
+        if (g > total) g = total;
+        if (g < 1) g = 1;
+        return dim3((unsigned)g, 1, 1);
+    }
+
     int setup(Backend* b, int lanes, int nq_) override
     {
         be = b;
+        persistent = false;
+        if (const char* e = getenv("TWSTFT_PERSISTENT")) persistent = atoi(e) != 0;
         max_lanes = lanes;
         nq = nq_;
         std::vector<float2> blob(CS::BLOB + RS::BLOB + 4);
@@ -138,12 +151,15 @@ public:
     int build_code(const unsigned char* d_bits, int rep, int qpsk, float2 mean) override
     {
         ColParams c{};
-        c.src = d_bits; c.dst = d_A; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.nch = 1;
-        c.rep = rep; c.qpsk = qpsk; c.code_mean = mean; c.nq = 1;
-        be->template launch<KCol<CS, TS, SRC_BITS, COL_FWD>>(dim3(NCOLTILE, 1, 1), c);
+        c.src = d_bits; c.dst = d_A; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.invN = 1.0 / (double)N; c.nch = 1;
+        c.rep = rep; c.qpsk = qpsk; c.code_mean = mean; c.nq = 1; c.ntx = NCOLTILE; c.ny = 1;
+        typedef KCol<CS, TS, SRC_BITS, COL_FWD> KC;
+        be->template launch<KC>(pgrid<KC>(NCOLTILE), c);
         RowParams r{};
-        r.src = d_A; r.dst = d_code; r.blob = d_blob_r; r.N = N; r.N1 = L1; r.nq = 1; r.nblk = NROWBLK;
-        be->template launch<KRow<RS, RPC, ROW_FWD_STORE>>(dim3(NROWBLK, 1, 1), r);
+        r.src = d_A; r.dst = d_code; r.blob = d_blob_r; r.N = N; r.N1 = L1; r.invN = 1.0 / (double)N; r.invM = 1.0 / ((double)nq * (double)N); r.nq = 1; r.nblk = NROWBLK;
+        r.nlanes = 1;
+        typedef KRow<RS, RPC, ROW_FWD_STORE> KR;
+        be->template launch<KR>(pgrid<KR>(NROWBLK), r);
         return be->ok() ? 0 : -1;
     }
 
@@ -160,13 +176,15 @@ public:
         be->template launch<KMean>(dim3(nblk, a.nrec, 1), m);
     }
 
-    void col_raw(const RunArgs& a, int op, int sub_mean)
+    template <int OP> void col_raw(const RunArgs& a, int sub_mean)
     {
         ColParams c{};
-        c.src = a.d_raw; c.dst = d_A; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.nch = a.nch;
-        c.op = op; c.sub_mean = sub_mean; c.sums = d_sums; c.lrow = d_lrow; c.lcol = d_lcol;
+        c.src = a.d_raw; c.dst = d_A; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.invN = 1.0 / (double)N; c.nch = a.nch;
+        c.sub_mean = sub_mean; c.sums = d_sums; c.lrow = d_lrow; c.lcol = d_lcol;
         c.rec_stride = a.rec_stride; c.rec_offset = a.d_rec_offset; c.nq = 1;
-        be->template launch<KCol<CS, TS, SRC_RAW, COL_FWD>>(dim3(NCOLTILE * a.nch, a.nrec, 1), c);
+        c.ntx = NCOLTILE * a.nch; c.ny = a.nrec;
+        typedef KCol<CS, TS, SRC_RAW, COL_FWD, OP> KC;
+        be->template launch<KC>(pgrid<KC>((i64)c.ntx * c.ny), c);
     }
 
     void df_final(const RunArgs& a, const EstimatorCfg* e)
@@ -187,11 +205,24 @@ public:
         if (lanes > max_lanes) return -2;
         if (e.sub_mean) means(a);
         have_means = e.sub_mean != 0;
-        col_raw(a, e.power, e.sub_mean);
+        if (e.power == 4) col_raw<4>(a, e.sub_mean);
+        else col_raw<2>(a, e.sub_mean);
         RowParams r{};
-        r.src = d_A; r.blob = d_blob_r; r.N = N; r.N1 = L1; r.win_lo = e.win_lo; r.win_hi = e.win_hi;
+        r.src = d_A; r.blob = d_blob_r; r.N = N; r.N1 = L1; r.invN = 1.0 / (double)N; r.invM = 1.0 / ((double)nq * (double)N); r.win_lo = e.win_lo; r.win_hi = e.win_hi;
         r.part_key = d_keyrow; r.nq = 1; r.nblk = NROWBLK;
-        be->template launch<KRow<RS, RPC, ROW_FWD_ARGMAX>>(dim3(NROWBLK, lanes, 1), r);
+        {   // k2 ranges whose bins k = k1 + L1*k2 can intersect the window (bins as signed frequencies)
+            const i64 ka = e.win_lo - N / 2, kb = e.win_hi - N / 2;     // signed bin range [ka, kb]
+            auto lo_of = [&](i64 k) { i64 v = (k - (L1 - 1)) / L1; if ((k - (L1 - 1)) < 0 && (k - (L1 - 1)) % L1) v--; return v; };
+            r.oa1 = 0; r.ob1 = -1; r.oa2 = 0; r.ob2 = -1;
+            if (ka >= 0) { r.oa1 = (int)lo_of(ka); r.ob1 = (int)(kb / L1); }
+            else if (kb < 0) { r.oa1 = (int)lo_of(ka + N); r.ob1 = (int)((kb + N) / L1); }
+            else { r.oa1 = 0; r.ob1 = (int)(kb / L1); r.oa2 = (int)lo_of(ka + N); r.ob2 = N2 - 1; }
+            if (r.oa1 < 0) r.oa1 = 0;
+            if (r.oa2 < 0) r.oa2 = 0;
+        }
+        r.nlanes = lanes;
+        typedef KRow<RS, RPC, ROW_FWD_ARGMAX> KR;
+        be->template launch<KR>(pgrid<KR>((i64)NROWBLK * lanes), r);
         df_final(a, &e);
         return be->ok() ? 0 : -1;
     }
@@ -204,18 +235,23 @@ public:
         if (!(a.estimate && have_means)) means(a);
         have_means = false;
         if (!a.estimate) df_final(a, nullptr);
-        col_raw(a, 1, 1);
+        col_raw<1>(a, 1);
         RowParams r{};
-        r.src = d_A; r.dst = d_P; r.blob = d_blob_r; r.N = N; r.N1 = L1; r.code = d_code;
+        r.src = d_A; r.dst = d_P; r.blob = d_blob_r; r.N = N; r.N1 = L1; r.invN = 1.0 / (double)N; r.invM = 1.0 / ((double)nq * (double)N); r.code = d_code;
         r.conj_mode = a.variant; r.part_energy = d_energy; r.y0 = d_y0; r.nq = 1; r.nblk = NROWBLK;
-        be->template launch<KRow<RS, RPC, ROW_FWD_MULCODE>>(dim3(NROWBLK, lanes, 1), r);
+        r.nlanes = lanes;
+        typedef KRow<RS, RPC, ROW_FWD_MULCODE> KRM;
+        be->template launch<KRM>(pgrid<KRM>((i64)NROWBLK * lanes), r);
         RowParams t{};
-        t.src = d_P; t.dst = d_B; t.blob = d_blob_r; t.N = N; t.N1 = L1; t.twq = d_twq; t.nq = nq; t.nblk = NROWBLK;
-        be->template launch<KRow<RS, RPC, ROW_INV_TWIST>>(dim3(NROWBLK, lanes, nq), t);
+        t.src = d_P; t.dst = d_B; t.blob = d_blob_r; t.N = N; t.N1 = L1; t.invN = 1.0 / (double)N; t.invM = 1.0 / ((double)nq * (double)N); t.twq = d_twq; t.nq = nq; t.nblk = NROWBLK;
+        t.nlanes = lanes;
+        typedef KRow<RS, RPC, ROW_INV_TWIST> KRI;
+        be->template launch<KRI>(pgrid<KRI>((i64)NROWBLK * nq * lanes), t);
         ColParams c{};
-        c.src = d_B; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.nch = 1; c.nq = nq; c.part_key = d_keycol;
-        c.ntile = NCOLTILE;
-        be->template launch<KCol<CS, TS, SRC_CF32, COL_INV_ARGMAX>>(dim3(NCOLTILE, lanes * nq, 1), c);
+        c.src = d_B; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.invN = 1.0 / (double)N; c.nch = 1; c.nq = nq; c.part_key = d_keycol;
+        c.ntx = NCOLTILE; c.ny = lanes * nq;
+        typedef KCol<CS, TS, SRC_CF32, COL_INV_ARGMAX> KCI;
+        be->template launch<KCI>(pgrid<KCI>((i64)c.ntx * c.ny), c);
         PeakTabParams pt{};
         pt.part_key = d_keycol; pt.npart = nq * NCOLTILE; pt.N = N; pt.nq = nq; pt.L1 = L1; pt.N2 = N2;
         pt.p0_out = d_p0; pt.rowph = d_rowph; pt.wk2 = d_wk2; pt.nsplit = 16;

@@ -10,9 +10,13 @@
 namespace twstft {
 
 template <class K, int PH> struct EmuPhases {
-    static void run(const typename K::Params& p, const Blk& b, std::vector<typename K::Regs>& regs, unsigned char* smem)
+    static void run(const typename K::Params& p, const Blk& b, std::vector<typename K::Regs>& regs, unsigned char* smem,
+                    int it, int nit)
     {
-        for (int tid = 0; tid < K::NT; tid++) K::template phase<PH>(p, b, tid, regs[tid], smem);
+        for (int tid = 0; tid < K::NT; tid++) {
+            if constexpr (K::PERSISTENT) K::template phase<PH>(p, b, tid, regs[tid], smem, it, nit);
+            else K::template phase<PH>(p, b, tid, regs[tid], smem);
+        }
         if constexpr (PH + 1 < K::NPH) {
             constexpr int kind = K::sync_after(PH);
             if constexpr (kind == SYNC_MAXKEY || kind == SYNC_MAXKEY_SUMD) {
@@ -27,7 +31,7 @@ template <class K, int PH> struct EmuPhases {
                     regs[0].dsum[i] = t;
                 }
             }
-            EmuPhases<K, PH + 1>::run(p, b, regs, smem);
+            EmuPhases<K, PH + 1>::run(p, b, regs, smem, it, nit);
         }
     }
 };
@@ -35,6 +39,7 @@ template <class K, int PH> struct EmuPhases {
 struct Backend {
     static constexpr bool is_emulation = true;
     int device = 0;
+    int num_sms = 3;     // small on purpose: persistent kernels then loop several times per CTA
     int err = 0;
     long launches = 0;
     bool ok() const { return err == 0; }
@@ -61,8 +66,13 @@ struct Backend {
         for (unsigned z = 0; z < grid.z; z++)
             for (unsigned y = 0; y < grid.y; y++)
                 for (unsigned x = 0; x < grid.x; x++) {
-                    Blk b{(int)x, (int)y, (int)z};
-                    EmuPhases<K, 0>::run(p, b, regs, smem.data());
+                    Blk b{(int)x, (int)y, (int)z, (int)grid.x};
+                    if constexpr (K::PERSISTENT) {
+                        const int nit = K::niter(p, (int)x, (int)grid.x);
+                        for (int it = 0; it < nit; it++) EmuPhases<K, 0>::run(p, b, regs, smem.data(), it, nit);
+                    } else {
+                        EmuPhases<K, 0>::run(p, b, regs, smem.data(), 0, 1);
+                    }
                 }
         launches++;
     }
