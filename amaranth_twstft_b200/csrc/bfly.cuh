@@ -23,12 +23,13 @@ template <> struct Bfly<2> {
 template <> struct Bfly<4> {
     static HD void run(float2* v)
     {
-        float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
-        float2 t2 = cadd(v[1], v[3]), t3 = csub(v[1], v[3]);
+        const float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+        const float2 t2 = cadd(v[1], v[3]);
+        const float2 t3r = make_float2(v[1].y - v[3].y, v[3].x - v[1].x);   // -i*(v1 - v3)
         v[0] = cadd(t0, t2);
         v[2] = csub(t0, t2);
-        v[1] = make_float2(t1.x + t3.y, t1.y - t3.x);   // t1 - i*t3
-        v[3] = make_float2(t1.x - t3.y, t1.y + t3.x);   // t1 + i*t3
+        v[1] = cadd(t1, t3r);   // t1 - i*t3
+        v[3] = csub(t1, t3r);   // t1 + i*t3
     }
 };
 
@@ -37,17 +38,18 @@ template <> struct Bfly<5> {
     {
         const float c1 = 0.30901699437494745f, c2 = -0.8090169943749473f;
         const float s1 = 0.9510565162951535f, s2 = 0.5877852522924732f;
-        float2 t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]);
-        float2 t3 = csub(v[1], v[4]), t4 = csub(v[2], v[3]);
-        float2 a1 = make_float2(v[0].x + c1 * t1.x + c2 * t2.x, v[0].y + c1 * t1.y + c2 * t2.y);
-        float2 a2 = make_float2(v[0].x + c2 * t1.x + c1 * t2.x, v[0].y + c2 * t1.y + c1 * t2.y);
-        float2 b1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
-        float2 b2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
-        v[0] = make_float2(v[0].x + t1.x + t2.x, v[0].y + t1.y + t2.y);
-        v[1] = make_float2(a1.x + b1.y, a1.y - b1.x);   // a1 - i*b1
-        v[4] = make_float2(a1.x - b1.y, a1.y + b1.x);   // a1 + i*b1
-        v[2] = make_float2(a2.x + b2.y, a2.y - b2.x);
-        v[3] = make_float2(a2.x - b2.y, a2.y + b2.x);
+        const float2 t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]);
+        const float2 t3r = make_float2(v[1].y - v[4].y, v[4].x - v[1].x);   // -i*(v1 - v4)
+        const float2 t4r = make_float2(v[2].y - v[3].y, v[3].x - v[2].x);   // -i*(v2 - v3)
+        const float2 a1 = caxpy(c2, t2, caxpy(c1, t1, v[0]));
+        const float2 a2 = caxpy(c1, t2, caxpy(c2, t1, v[0]));
+        const float2 b1 = caxpy(s2, t4r, cscale(s1, t3r));      // -i*(s1*t3 + s2*t4)
+        const float2 b2 = caxpy(-s1, t4r, cscale(s2, t3r));     // -i*(s2*t3 - s1*t4)
+        v[0] = cadd(v[0], cadd(t1, t2));
+        v[1] = cadd(a1, b1);
+        v[4] = csub(a1, b1);
+        v[2] = cadd(a2, b2);
+        v[3] = csub(a2, b2);
     }
 };
 
@@ -61,7 +63,8 @@ template <int R> HD float2 mul_root(float2 a, int t)
     if ((R % 4 == 0) && t == 3 * R / 4) return make_float2(-a.y, a.x);   // * (+i)
     float c, s;
     UnitRoots<R>::get(t, c, s);
-    return make_float2(a.x * c + a.y * s, a.y * c - a.x * s);            // a * (c - i s)
+    const float2 m = cscale(c, a);                                       // a * (c - i s)
+    return make_float2(m.x + a.y * s, m.y - a.x * s);
 }
 
 // R = RA*RB: n = na*RB + nb, k = ka + RA*kb

@@ -24,11 +24,74 @@ struct Blk { int x, y, z, gx; };   // block index and gridDim.x
 enum SyncKind { SYNC_BARRIER = 0, SYNC_MAXKEY = 1, SYNC_SUMD = 2, SYNC_MAXKEY_SUMD = 3 };
 
 // ------------------------------------------------------------------ complex fp32 helpers
+// On sm_100a a complex value lives in an aligned 64-bit register pair and the arithmetic uses the
+// packed fp32x2 instructions (FADD2 / FMUL2 / FFMA2): same FP32 pipe throughput as the scalar forms
+// (measured, tools/ubench/fp32x2.cu) but half the issue slots, which is what bounds the FFT passes.
+// pk()/upk() are register renames for ptxas.  The host build (test emulation) uses plain floats.
 HD float2 cf(float x, float y) { return make_float2(x, y); }
-HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-HD float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a*conj(b)
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ u64 pk(float2 a) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r; }
+__device__ __forceinline__ u64 pk(float x, float y) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
+__device__ __forceinline__ float2 upk(u64 v) { float2 r; asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+#endif
+HD float2 cadd(float2 a, float2 b)
+{
+#ifdef __CUDA_ARCH__
+    return upk(add2(pk(a), pk(b)));
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+HD float2 csub(float2 a, float2 b)
+{
+#ifdef __CUDA_ARCH__
+    return upk(sub2(pk(a), pk(b)));
+#else
+    return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
+// s * a (real scalar)
+HD float2 cscale(float s, float2 a)
+{
+#ifdef __CUDA_ARCH__
+    return upk(mul2(pk(s, s), pk(a)));
+#else
+    return make_float2(s * a.x, s * a.y);
+#endif
+}
+// s * a + b (real scalar s)
+HD float2 caxpy(float s, float2 a, float2 b)
+{
+#ifdef __CUDA_ARCH__
+    return upk(fma2(pk(s, s), pk(a), pk(b)));
+#else
+    return make_float2(s * a.x + b.x, s * a.y + b.y);
+#endif
+}
+// a*b: one packed multiply by the broadcast real part, two scalar FMAs for the imaginary part
+HD float2 cmul(float2 a, float2 b)
+{
+#ifdef __CUDA_ARCH__
+    const float2 t = upk(mul2(pk(a.x, a.x), pk(b)));
+    return make_float2(fmaf(-a.y, b.y, t.x), fmaf(a.y, b.x, t.y));
+#else
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+#endif
+}
+// a*conj(b)
+HD float2 cmulc(float2 a, float2 b)
+{
+#ifdef __CUDA_ARCH__
+    const float2 t = upk(mul2(pk(b.x, b.x), pk(a)));
+    return make_float2(fmaf(a.y, b.y, t.x), fmaf(-a.x, b.y, t.y));
+#else
+    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+#endif
+}
 HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 HD float2 cswap(float2 a) { return make_float2(a.y, a.x); }
 HD float cnorm(float2 a) { return a.x * a.x + a.y * a.y; }

@@ -1,0 +1,245 @@
+// Fused correlator row pass: for one row k1 of the (transposed-order) spectrum and one lane,
+//   forward row FFT  ->  P = Y*conj(C) (G) / conj(Y)*C (K), sum|Y|^2, Y[0]
+//   -> for every polyphase q of the x3 interpolation: twist, inverse row FFT, conjugate four-step
+//      twiddle, store B[lane][q][k1][n2].
+// Replaces  ffty=fft(y); prnmap=ifft([P(1:N/2) zeros(2N) P(N/2+1:N)])  of the reference
+//   processing/Octave/godual_ranging.m:25-28, acquisition/claudio_aligned_code_lo_separate.m:29,34-36
+// for the row half of the four-step transforms.
+//
+// The product spectrum P never goes to HBM.  The last forward stage leaves thread j with the bins
+// k2 = j + m*SP0, which are exactly the stage-0 operands of the inverse transforms (R0 == RLAST), so
+// P is a per-thread quantity.  It has to survive three inverse transforms, but neither the register
+// file (two 416-thread CTAs per SM leave 78 registers per thread) nor shared memory (the exchange
+// buffers fill it) has room for it: it is parked in Blackwell's TENSOR MEMORY with tcgen05.st and
+// fetched back with tcgen05.ld (12-cycle latency, per-CTA private) -- TMEM used as a software-managed
+// register spill space, no tensor-core instruction involved.
+#pragma once
+#include "fft_core.cuh"
+
+namespace twstft {
+
+// ---- TMEM park/fetch of a thread's E complex values (device) / plain array (test emulation) ----
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void tmem_st8(unsigned a, const unsigned* s)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(a), "r"(s[0]), "r"(s[1]),
+                 "r"(s[2]), "r"(s[3]), "r"(s[4]), "r"(s[5]), "r"(s[6]), "r"(s[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(unsigned a, unsigned* d)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7])
+                 : "r"(a) : "memory");
+}
+// this warp's window: lanes 32*(warp%4).., columns (warp/4)*NCOL..
+template <int NCOL> __device__ __forceinline__ unsigned tmem_window(unsigned base)
+{
+    const unsigned warp = threadIdx.x >> 5;
+    return base + (((warp & 3u) * 32u) << 16) + (warp >> 2) * NCOL;
+}
+template <int E> __device__ __forceinline__ void tmem_park(unsigned base, const float2* v)
+{
+    static_assert((2 * E) % 8 == 0, "TMEM transfers move 8 columns at a time");
+    unsigned w[2 * E];
+#pragma unroll
+    for (int i = 0; i < E; i++) { w[2 * i] = __float_as_uint(v[i].x); w[2 * i + 1] = __float_as_uint(v[i].y); }
+    const unsigned a = tmem_window<2 * E>(base);
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 2 * E; c += 8) tmem_st8(a + c, w + c);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+template <int E> __device__ __forceinline__ void tmem_fetch(unsigned base, float2* v)
+{
+    unsigned w[2 * E];
+    const unsigned a = tmem_window<2 * E>(base);
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 2 * E; c += 8) tmem_ld8(a + c, w + c);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < E; i++) v[i] = make_float2(__uint_as_float(w[2 * i]), __uint_as_float(w[2 * i + 1]));
+}
+#endif
+
+constexpr int tmem_pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
+
+struct RowCorrParams {
+    const float2* src;       // A [lane][N1][L]
+    float2* dst;             // B [lane][nq][N1][L]
+    const float2* blob;      // S::BLOB twiddle entries
+    const float2* code;      // C [N1][L] (transposed order)
+    const float2* qconst;    // [nq][R0]: exp(2 pi i q m/(nq R0)) * (m >= R0/2 ? exp(-2 pi i q/nq) : 1)
+    i64 N;                   // N1 * L
+    int N1;
+    double invN, invM;       // 1/N, 1/(nq*N)
+    int nlanes;
+    int nblk;                // row groups per lane (N1 / RPC)
+    int conj_mode;           // 0: Y*conj(C) (variant G)   1: conj(Y)*C (variant K)
+    double* part_energy;     // [lane][nblk]  sum |Y|^2
+    float2* y0;              // [lane] Y[0]
+};
+
+template <class S, int RPC, int NQ> struct KRowCorr {
+    typedef RowCorrParams Params;
+    static const char* name() { return "row_corr"; }
+    static_assert(S::NSTAGE >= 2, "row transforms have at least two stages");
+    static_assert(S::R0 == S::RLAST && S::SP0 == S::NSLAST, "forward outputs must be the inverse stage-0 operands");
+    static_assert(S::R0 % 2 == 0, "negative-frequency split needs an even first radix");
+    static constexpr bool PERSISTENT = true;
+    static constexpr int NST = S::NSTAGE;
+    static constexpr int NTA = S::NTS * RPC;
+    static constexpr int NT = (NTA + 31) / 32 * 32;
+    static constexpr int MINB = (S::L * RPC >= 8000) ? 2 : 4;
+    // TMEM: 2*E columns per warp slot, four warps (one per lane quarter) share a slot
+    static constexpr int TMEM_COLS = tmem_pow2_cols(((NT / 32 + 3) / 4) * 2 * S::E);
+    static_assert(((NT / 32 + 3) / 4) * 2 * S::E <= 512 / MINB, "parked spectrum does not fit the CTA's share of TMEM");
+    typedef RowAcc<S::SP0> Acc;
+    static constexpr int ROWSM = (S::R0 * Acc::BSTRIDE + 1) & ~1;
+    static constexpr int NQC = (NQ * S::R0 + 1) & ~1;
+    static constexpr int NG = RPC * S::RLAST;
+    static constexpr int OFF_QC = S::BLOB_PAD;
+    static constexpr int OFF_G = OFF_QC + NQC;
+    static constexpr int OFF_DATA = OFF_G + ((NG + 1) & ~1);
+    static constexpr int NPH = NST * (1 + NQ);
+    static constexpr int NSUM = 1;
+    static constexpr int NBL = (S::L / S::RLAST) / S::NTS;
+    static constexpr int NB0 = S::SP0 / S::NTS;
+    static_assert(NBL == NB0, "butterflies per thread must match between the first and the last stage");
+    struct Regs {
+        float2 v[S::E];
+        u64 key;
+        double dsum[NSUM];
+        unsigned tmem;       // TMEM base address of this CTA (device)
+#ifdef TWSTFT_EMU
+        float2 P[S::E];      // host emulation: the parked spectrum
+#endif
+    };
+    static HD constexpr size_t smem_bytes()
+    {
+        return (size_t)(OFF_DATA + RPC * ROWSM) * sizeof(float2) + RED_SCRATCH_BYTES;
+    }
+    static HD constexpr int sync_after(int ph) { return ph == NST - 1 ? SYNC_SUMD : SYNC_BARRIER; }
+
+    // work item w = (rowblk = w / nlanes, lane = w % nlanes): CTAs that run together share the code row in L2
+    static HD int niter(const Params& p, int bx, int gdim)
+    {
+        const i64 total = (i64)p.nblk * p.nlanes;
+        return bx < total ? (int)((total - bx + gdim - 1) / gdim) : 0;
+    }
+    struct Work { int rowblk; i64 lane; };
+    static HD Work work_of(const Params& p, const Blk& blk, int it)
+    {
+        const i64 w = (i64)blk.x + (i64)it * blk.gx;
+        Work k;
+        k.rowblk = (int)(w / p.nlanes);
+        k.lane = w % p.nlanes;
+        return k;
+    }
+
+    static HD void park(Regs& r)
+    {
+#if defined(__CUDA_ARCH__)
+        tmem_park<S::E>(r.tmem, r.v);
+#elif defined(TWSTFT_EMU)
+        for (int i = 0; i < S::E; i++) r.P[i] = r.v[i];
+#endif
+    }
+    static HD void fetch(Regs& r)
+    {
+#if defined(__CUDA_ARCH__)
+        tmem_fetch<S::E>(r.tmem, r.v);
+#elif defined(TWSTFT_EMU)
+        for (int i = 0; i < S::E; i++) r.v[i] = r.P[i];
+#endif
+    }
+
+    template <int PH>
+    static HD void phase(const Params& p, const Blk& blk, int tid, Regs& r, unsigned char* smem, int it, int nit)
+    {
+        constexpr int F = PH / NST, ST = PH % NST;     // F = 0 forward, F = q+1 inverse
+        float2* sm = reinterpret_cast<float2*>(smem);
+        const bool active = tid < NTA;                 // the TMEM transfers below are warp-wide: idle threads take part
+        const int rl = active ? tid / S::NTS : 0, j = tid % S::NTS;
+        const Acc acc{sm + OFF_DATA + rl * ROWSM};
+        const Work wk = work_of(p, blk, it);
+        const int row = wk.rowblk * RPC + rl;
+        float2* gtab = sm + OFF_G;
+
+        if (PH == 0) {
+            r.key = 0;
+            r.dsum[0] = 0.0;
+            if (active) {
+                if (it == 0) {
+                    for (int i = tid; i < S::BLOB; i += NTA) sm[i] = p.blob[i];
+                    for (int i = tid; i < NQ * S::R0; i += NTA) sm[OFF_QC + i] = p.qconst[i];
+                }
+                for (int t = tid; t < NG; t += NTA) {      // conjugate four-step twiddle steps of this item's rows
+                    const int rl2 = t / S::RLAST, m = t % S::RLAST;
+                    const i64 row2 = (i64)wk.rowblk * RPC + rl2;
+                    gtab[t] = cis_cycles((double)(row2 * S::NSLAST * m) * p.invN);
+                }
+                const float2* xj = p.src + wk.lane * p.N + (i64)row * S::L + j;
+#pragma unroll
+                for (int b = 0; b < NB0; b++)
+#pragma unroll
+                    for (int m = 0; m < S::R0; m++) r.v[b * S::R0 + m] = xj[S::NTS * b + m * S::SP0];
+                dif_stage0<S>(j, r.v, p.blob, acc);
+            }
+        }
+        if (F > 0 && ST == 0) {
+            constexpr int q = F - 1;
+            if (q > 0) fetch(r);                          // q == 0: P is still in v
+            if (active) {
+                if (q == 0 && tid == 0) p.part_energy[wk.lane * p.nblk + wk.rowblk] = r.dsum[0];
+#pragma unroll
+                for (int b = 0; b < NB0; b++) {
+                    if (q == 0) {
+#pragma unroll
+                        for (int m = 0; m < S::R0; m++) r.v[b * S::R0 + m] = cswap(r.v[b * S::R0 + m]);
+                    } else {
+                        const int jb = j + S::NTS * b;
+                        const float2 base = cis_cycles((double)((i64)q * ((i64)row + (i64)p.N1 * jb)) * p.invM);
+                        const float2* qc = sm + OFF_QC + q * S::R0;
+#pragma unroll
+                        for (int m = 0; m < S::R0; m++)
+                            r.v[b * S::R0 + m] = cswap(cmul(r.v[b * S::R0 + m], cmul(base, qc[m])));
+                    }
+                }
+                dif_stage0<S>(j, r.v, sm, acc);
+            }
+        }
+        if (NST == 3 && ST == 1 && active) dif_stage_mid<S>(j, r.v, sm, acc);
+        if (ST == NST - 1) {
+            if (active) {
+                dif_stage_last<S>(j, r.v, acc);
+                if (F == 0) {
+                    float e = 0.f;
+                    const int cm = p.conj_mode;
+                    const float2* c = p.code + (i64)row * S::L;
+                    if (row == 0 && j == 0) p.y0[wk.lane] = r.v[0];
+                    last_stage_visit<S>(j, r.v, [&](int o, float2 x, int b, int m) {
+                        const float2 cc = c[o];
+                        e += cnorm(x);
+                        r.v[b * S::R0 + m] = cm ? cmul(cconj(x), cc) : cmulc(x, cc);
+                    });
+                    r.dsum[0] = (double)e;
+                } else {
+                    constexpr int q = F - 1;
+                    float2* d = p.dst + (wk.lane * NQ + q) * p.N + (i64)row * S::L;
+                    const float2* gr = gtab + rl * S::RLAST;
+                    float2 base[NBL];
+#pragma unroll
+                    for (int b = 0; b < NBL; b++)
+                        base[b] = cis_cycles((double)((i64)row * (j + S::NTS * b)) * p.invN);
+                    last_stage_visit<S>(j, r.v, [&](int o, float2 x, int b, int m) {
+                        d[o] = cmul(cswap(x), cmul(base[b], gr[m]));
+                    });
+                }
+            }
+            if (F == 0 && NQ > 1) park(r);                // P -> tensor memory for the polyphases q >= 1
+        }
+    }
+};
+
+}  // namespace twstft

@@ -168,34 +168,36 @@ struct KDfFinal {
 // ------------------------------------------------------------------------------------------------
 // Peak refinement.  With P the (transposed-order) product spectrum, the interpolated correlation is
 //   prnmap[p] = (1/M) sum_k P[k] exp(2 pi i ktilde p / M),  M = nq*N, ktilde = k - N for k >= N/2
-// (godual_ranging.m:26-28).  Around the coarse maximum p0 found by the fp32 inverse FFT we evaluate
-// NPTS points p0+DLO .. p0+DLO+NPTS-1 exactly (fp64 accumulation, fp64 phase reduction):
-//   k = k1 + L1*k2  ->  exp(..) = rowph[d][k1] * wk2[d][k2]
+// (godual_ranging.m:26-28).  Around the coarse maximum p0 found by the fp32 inverse FFT we re-evaluate
+// NPTS points p0+DLO .. p0+DLO+NPTS-1 from the inverse row-pass output with fp64 accumulation.
 constexpr int PEAK_NPTS = 7;
 constexpr int PEAK_DLO = -4;
 
-struct PeakTabParams {
-    const u64* part_key;   // [lane][npart]
+struct PeakEvalParams {
+    const u64* part_key;   // [lane][npart] first-max keys of the column-pass tiles
     int npart;
+    const float2* B;       // [lane][nq][L1][N2] inverse row-pass output
     i64 N;
     int nq;
     int L1, N2;
     i64* p0_out;           // [lane]
-    float2* rowph;         // [lane][NPTS][L1]
-    float2* wk2;           // [lane][NPTS][N2]
-    int nsplit;
+    double* part;          // [lane][NPTS][2]
 };
-struct KPeakTables {
-    typedef PeakTabParams Params;
-    static const char* name() { return "peak_tables"; }
+// One CTA per (lag, lane): prnmap[p] = sum_k1 B[q][k1][n2] exp(+2 pi i k1 n1 / L1) with
+// p = nq*(n1*N2 + n2) + q, i.e. one output of the inverse column transform evaluated directly
+// (fp64 twiddles and accumulation) -- a few thousand terms instead of a pass over the spectrum.
+struct KPeakEval {
+    typedef PeakEvalParams Params;
+    static const char* name() { return "peak_eval"; }
     static constexpr bool PERSISTENT = false;
-    static constexpr int NT = 256, MINB = 4, NPH = 2, NSUM = 1;
+    static constexpr int NT = 128, MINB = 4, NPH = 3, NSUM = 2;
     struct Regs { u64 key; double dsum[NSUM]; };
     static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }
-    static HD constexpr int sync_after(int) { return SYNC_MAXKEY; }
+    static HD constexpr int sync_after(int ph) { return ph == 0 ? SYNC_MAXKEY : SYNC_SUMD; }
     template <int PH> static HD void phase(const Params& p, const Blk& blk, int tid, Regs& r, unsigned char*)
     {
         const i64 lane = blk.y;
+        const int d = blk.x;
         if (PH == 0) {
             u64 best = 0;
             for (int i = tid; i < p.npart; i += NT) {
@@ -203,97 +205,29 @@ struct KPeakTables {
                 best = k > best ? k : best;
             }
             r.key = best;
-            r.dsum[0] = 0.0;
-        } else {
+            r.dsum[0] = r.dsum[1] = 0.0;
+        } else if (PH == 1) {
             const i64 M = (i64)p.nq * p.N;
             const i64 p0 = (i64)key_index(r.key);
-            if (blk.x == 0 && tid == 0) p.p0_out[lane] = p0;
-            const int per = p.L1 + p.N2;
-            const int tot = PEAK_NPTS * per;
-            const double invM = 1.0 / (double)M;
-            for (int e = blk.x * NT + tid; e < tot; e += p.nsplit * NT) {
-                const int d = e / per, rr = e % per;
-                i64 pp = (p0 + PEAK_DLO + d) % M;
-                if (pp < 0) pp += M;
-                if (rr < p.L1) {
-                    const i64 x = ((i64)rr * pp) % M;
-                    p.rowph[(lane * PEAK_NPTS + d) * p.L1 + rr] = cis_cycles((double)x * invM);
-                } else {
-                    const int k2 = rr - p.L1;
-                    const i64 x = (((i64)p.L1 * k2) % M * pp) % M;
-                    double c = (double)x * invM;
-                    if (k2 >= p.N2 / 2) c -= (double)((p.N % M) * pp % M) * invM;
-                    p.wk2[(lane * PEAK_NPTS + d) * p.N2 + k2] = cis_cycles(c);
-                }
+            i64 pp = (p0 + PEAK_DLO + d) % M;
+            if (pp < 0) pp += M;
+            const int q = (int)(pp % p.nq);
+            const i64 m = pp / p.nq;
+            const i64 n1 = m / p.N2, n2 = m % p.N2;
+            const float2* src = p.B + ((lane * p.nq + q) * p.L1) * (i64)p.N2 + n2;
+            double sr = 0.0, si = 0.0;
+            for (int k1 = tid; k1 < p.L1; k1 += NT) {
+                const float2 x = src[(i64)k1 * p.N2];
+                const double2 w = cis_cycles_d((double)((k1 * n1) % p.L1) / (double)p.L1);
+                sr += (double)x.x * w.x - (double)x.y * w.y;
+                si += (double)x.x * w.y + (double)x.y * w.x;
             }
-        }
-    }
-};
-
-struct PeakSumParams {
-    const float2* P;       // [lane][N]
-    const float2* rowph;   // [lane][NPTS][L1]
-    const float2* wk2;     // [lane][NPTS][N2]
-    i64 N;
-    int L1, N2;
-    double* part;          // [lane][nblk][2*NPTS]
-    int nblk;
-};
-template <int L1MAX> struct KPeakSums {
-    typedef PeakSumParams Params;
-    static const char* name() { return "peak_sums"; }
-    static constexpr int KW = 16;                 // k2 columns per CTA
-    static constexpr bool PERSISTENT = false;
-    static constexpr int NT = 256, MINB = 2, NPH = 3, NSUM = 2 * PEAK_NPTS;
-    static constexpr int NGRP = NT / KW;
-    struct Regs { u64 key; double dsum[NSUM]; };
-    static HD constexpr size_t smem_bytes() { return (size_t)PEAK_NPTS * L1MAX * sizeof(float2) + RED_SCRATCH_BYTES; }
-    static HD constexpr int sync_after(int ph) { return ph == 0 ? SYNC_BARRIER : SYNC_SUMD; }
-    template <int PH> static HD void phase(const Params& p, const Blk& blk, int tid, Regs& r, unsigned char* smem)
-    {
-        float2* rp = reinterpret_cast<float2*>(smem);
-        const i64 lane = blk.y;
-        if (PH == 0) {
-            const float2* src = p.rowph + lane * PEAK_NPTS * p.L1;
-            for (int i = tid; i < PEAK_NPTS * p.L1; i += NT) rp[i] = src[i];
-        } else if (PH == 1) {
-            const int kl = tid % KW, g = tid / KW;
-            const int k2 = blk.x * KW + kl;
-            const float2* src = p.P + lane * p.N + k2;
-            float2 acc[PEAK_NPTS];
-#pragma unroll
-            for (int d = 0; d < PEAK_NPTS; d++) acc[d] = make_float2(0.f, 0.f);
-            constexpr int BATCH = 10;     // loads in flight per thread
-            for (int k1b = g; k1b < p.L1; k1b += NGRP * BATCH) {
-                float2 x[BATCH];
-#pragma unroll
-                for (int u = 0; u < BATCH; u++) {
-                    const int k1 = k1b + u * NGRP;
-                    x[u] = (k1 < p.L1) ? src[(i64)k1 * p.N2] : make_float2(0.f, 0.f);
-                }
-#pragma unroll
-                for (int u = 0; u < BATCH; u++) {
-                    const int k1 = k1b + u * NGRP;
-                    if (k1 < p.L1) {
-#pragma unroll
-                        for (int d = 0; d < PEAK_NPTS; d++) {
-                            const float2 w = rp[d * p.L1 + k1];
-                            acc[d].x += x[u].x * w.x - x[u].y * w.y;
-                            acc[d].y += x[u].x * w.y + x[u].y * w.x;
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int d = 0; d < PEAK_NPTS; d++) {
-                const float2 w = p.wk2[(lane * PEAK_NPTS + d) * p.N2 + k2];
-                r.dsum[2 * d] = (double)acc[d].x * (double)w.x - (double)acc[d].y * (double)w.y;
-                r.dsum[2 * d + 1] = (double)acc[d].x * (double)w.y + (double)acc[d].y * (double)w.x;
-            }
+            r.dsum[0] = sr;
+            r.dsum[1] = si;
         } else if (tid == 0) {
-            double* o = p.part + (lane * p.nblk + blk.x) * NSUM;
-#pragma unroll
-            for (int i = 0; i < NSUM; i++) o[i] = r.dsum[i];
+            p.part[(lane * PEAK_NPTS + d) * 2] = r.dsum[0];
+            p.part[(lane * PEAK_NPTS + d) * 2 + 1] = r.dsum[1];
+            if (d == 0) p.p0_out[lane] = (i64)key_index(r.key);
         }
     }
 };

@@ -74,11 +74,29 @@ __device__ __forceinline__ void run_phases(const typename K::Params& p, const Bl
     }
 }
 
+// Kernels that park per-thread data in tensor memory declare K::TMEM_COLS (a power of two >= 32) and a
+// `unsigned tmem` member in K::Regs; warp 0 allocates the columns once per CTA and frees them at the end.
+template <class K, class = void> struct TmemCols { static constexpr int value = 0; };
+template <class K> struct TmemCols<K, decltype((void)K::TMEM_COLS)> { static constexpr int value = K::TMEM_COLS; };
+
 template <class K> __global__ void __launch_bounds__(K::NT, K::MINB) kernel_entry(const typename K::Params p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     typename K::Regs r;
     Blk b{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z, (int)gridDim.x};
+    constexpr int TC = TmemCols<K>::value;
+    if constexpr (TC > 0) {
+        __shared__ unsigned tmem_slot;
+        if (threadIdx.x < 32) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             (unsigned)__cvta_generic_to_shared(&tmem_slot)), "r"(TC) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        r.tmem = tmem_slot;
+    }
     if constexpr (K::PERSISTENT) {
         const int nit = K::niter(p, (int)blockIdx.x, (int)gridDim.x);
         for (int it = 0; it < nit; it++) {
@@ -87,6 +105,12 @@ template <class K> __global__ void __launch_bounds__(K::NT, K::MINB) kernel_entr
         }
     } else {
         run_phases<K, 0>(p, b, (int)threadIdx.x, r, smem, 0, 1);
+    }
+    if constexpr (TC > 0) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x < 32)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(r.tmem), "r"(TC) : "memory");
     }
 }
 

@@ -2,9 +2,9 @@
 //
 //   KMean                       exact window means                          godual_ranging.m:80,94
 //   KCol<RAW,FWD>(x^p) + KRow<FWD_ARGMAX> + KDfFinal   carrier offset       godual_ranging.m:14-15
-//   KCol<RAW,FWD>(derotate) + KRow<FWD_MULCODE>        P = fft(y).*fcode    godual_ranging.m:17-26
-//   KRow<INV_TWIST> x nq + KCol<CF32,INV_ARGMAX>       x3 ifft + coarse max godual_ranging.m:27-29
-//   KPeakTables + KPeakSums + KPeakFinal                parabola, phase, SNR godual_ranging.m:30-48
+//   KCol<RAW,FWD>(derotate) + KRowCorr                 fft(y).*fcode, row half of the x3 ifft  godual_ranging.m:17-28
+//   KCol<CF32,INV_ARGMAX>                              column half of the x3 ifft + coarse max  godual_ranging.m:27-29
+//   KPeakEval + KPeakFinal                             parabola, phase, SNR godual_ranging.m:30-48
 //
 // The same code drives the CUDA backend (product) and the host emulation backend (tests only).
 #pragma once
@@ -14,6 +14,7 @@
 #include "backend.cuh"
 #include "k_row.cuh"
 #include "k_col.cuh"
+#include "k_rowcorr.cuh"
 #include "k_small.cuh"
 
 namespace twstft {
@@ -60,33 +61,31 @@ public:
     static constexpr int L1 = CS::L, N2 = RS::L;
     static_assert(N2 % TS == 0 && (2 * N2) % TS == 0, "column tile must divide the row length");
     static_assert(L1 % RPC == 0, "rows per CTA must divide the column length");
-    static_assert(N2 % 16 == 0, "peak-sum tile");
     static_assert(N2 % 2 == 0, "negative-frequency split needs an even row length");
 
     Backend* be = nullptr;
     int max_lanes = 0, nq = 3;
     bool have_means = false;   // estimate() already left the window means in d_sums
-    float2 *d_blob_c = nullptr, *d_blob_r = nullptr, *d_code = nullptr, *d_twq = nullptr;
-    float2 *d_A = nullptr, *d_P = nullptr, *d_B = nullptr;
+    float2 *d_blob_c = nullptr, *d_blob_r = nullptr, *d_code = nullptr, *d_qconst = nullptr;
+    float2 *d_A = nullptr, *d_B = nullptr;
     double *d_sums = nullptr, *d_energy = nullptr, *d_df = nullptr, *d_peakpart = nullptr;
     u64 *d_keyrow = nullptr, *d_keycol = nullptr;
     i64 *d_sbin = nullptr, *d_p0 = nullptr;
-    float2 *d_y0 = nullptr, *d_lrow = nullptr, *d_lcol = nullptr, *d_rowph = nullptr, *d_wk2 = nullptr;
+    float2 *d_y0 = nullptr, *d_lrow = nullptr, *d_lcol = nullptr;
     static constexpr int NROWBLK = L1 / RPC;
     static constexpr int NCOLTILE = N2 / TS;
-    static constexpr int NPEAKBLK = N2 / 16;
 
     ~Pipe() override
     {
         if (!be) return;
-        void* all[] = {d_blob_c, d_blob_r, d_code, d_twq, d_A, d_P, d_B, d_sums, d_energy, d_df, d_peakpart,
-                       d_keyrow, d_keycol, d_sbin, d_p0, d_y0, d_lrow, d_lcol, d_rowph, d_wk2};
+        void* all[] = {d_blob_c, d_blob_r, d_code, d_qconst, d_A, d_B, d_sums, d_energy, d_df, d_peakpart,
+                       d_keyrow, d_keycol, d_sbin, d_p0, d_y0, d_lrow, d_lcol};
         for (void* p : all) be->free(p);
     }
     i64 size() const override { return N; }
     int col_len() const override { return L1; }
     int row_len() const override { return N2; }
-    size_t bytes_per_lane() const override { return (size_t)N * sizeof(float2) * (2 + nq); }
+    size_t bytes_per_lane() const override { return (size_t)N * sizeof(float2) * (1 + nq); }
 
     template <class T> T* dalloc(size_t n) { return reinterpret_cast<T*>(be->alloc(n * sizeof(T))); }
 
@@ -116,26 +115,26 @@ public:
         fill_blob<RS>(blob.data());
         be->h2d(d_blob_r, blob.data(), RS::BLOB * sizeof(float2));
         be->sync();
-        // per-k2 twist of polyphase q: exp(2 pi i q ktilde/(nq N)) without the per-row factor
-        std::vector<float2> tw((size_t)nq * N2);
+        // constant part of the polyphase twist exp(2 pi i q ktilde/(nq N)) for element m of a stage-0
+        // butterfly (k_rowcorr.cuh): exp(2 pi i q m/(nq R0)), times exp(-2 pi i q/nq) on the negative side
+        std::vector<float2> qc((size_t)nq * RS::R0);
         const double TWO_PI = 6.283185307179586476925287;
         for (int q = 0; q < nq; q++)
-            for (int k2 = 0; k2 < N2; k2++) {
-                double kt = (double)L1 * k2 - (k2 >= N2 / 2 ? (double)N : 0.0);
-                double a = TWO_PI * fmod((double)q * kt / ((double)nq * (double)N), 1.0);
-                tw[(size_t)q * N2 + k2] = make_float2((float)cos(a), (float)sin(a));
+            for (int m = 0; m < RS::R0; m++) {
+                double c = (double)(q * m) / ((double)nq * RS::R0) - (m >= RS::R0 / 2 ? (double)q / nq : 0.0);
+                c -= floor(c);
+                qc[(size_t)q * RS::R0 + m] = make_float2((float)cos(TWO_PI * c), (float)sin(TWO_PI * c));
             }
-        d_twq = dalloc<float2>((size_t)nq * N2);
-        be->h2d(d_twq, tw.data(), tw.size() * sizeof(float2));
+        d_qconst = dalloc<float2>(qc.size());
+        be->h2d(d_qconst, qc.data(), qc.size() * sizeof(float2));
         be->sync();
         d_code = dalloc<float2>(N);
         d_A = dalloc<float2>((size_t)lanes * N);
-        d_P = dalloc<float2>((size_t)lanes * N);
         d_B = dalloc<float2>((size_t)lanes * nq * N);
         d_sums = dalloc<double>((size_t)lanes * 2);
         d_energy = dalloc<double>((size_t)lanes * NROWBLK);
         d_df = dalloc<double>(lanes);
-        d_peakpart = dalloc<double>((size_t)lanes * NPEAKBLK * 2 * PEAK_NPTS);
+        d_peakpart = dalloc<double>((size_t)lanes * 2 * PEAK_NPTS);
         d_keyrow = dalloc<u64>((size_t)lanes * NROWBLK);
         d_keycol = dalloc<u64>((size_t)lanes * nq * NCOLTILE);
         d_sbin = dalloc<i64>(lanes);
@@ -143,8 +142,6 @@ public:
         d_y0 = dalloc<float2>(lanes);
         d_lrow = dalloc<float2>((size_t)lanes * L1);
         d_lcol = dalloc<float2>((size_t)lanes * N2);
-        d_rowph = dalloc<float2>((size_t)lanes * PEAK_NPTS * L1);
-        d_wk2 = dalloc<float2>((size_t)lanes * PEAK_NPTS * N2);
         return be->ok() ? 0 : -1;
     }
 
@@ -236,32 +233,30 @@ public:
         have_means = false;
         if (!a.estimate) df_final(a, nullptr);
         col_raw<1>(a, 1);
-        RowParams r{};
-        r.src = d_A; r.dst = d_P; r.blob = d_blob_r; r.N = N; r.N1 = L1; r.invN = 1.0 / (double)N; r.invM = 1.0 / ((double)nq * (double)N); r.code = d_code;
-        r.conj_mode = a.variant; r.part_energy = d_energy; r.y0 = d_y0; r.nq = 1; r.nblk = NROWBLK;
-        r.nlanes = lanes;
-        typedef KRow<RS, RPC, ROW_FWD_MULCODE> KRM;
-        be->template launch<KRM>(pgrid<KRM>((i64)NROWBLK * lanes), r);
-        RowParams t{};
-        t.src = d_P; t.dst = d_B; t.blob = d_blob_r; t.N = N; t.N1 = L1; t.invN = 1.0 / (double)N; t.invM = 1.0 / ((double)nq * (double)N); t.twq = d_twq; t.nq = nq; t.nblk = NROWBLK;
-        t.nlanes = lanes;
-        typedef KRow<RS, RPC, ROW_INV_TWIST> KRI;
-        be->template launch<KRI>(pgrid<KRI>((i64)NROWBLK * nq * lanes), t);
+        RowCorrParams r{};
+        r.src = d_A; r.dst = d_B; r.blob = d_blob_r; r.code = d_code; r.qconst = d_qconst; r.N = N; r.N1 = L1;
+        r.invN = 1.0 / (double)N; r.invM = 1.0 / ((double)nq * (double)N); r.nlanes = lanes; r.nblk = NROWBLK;
+        r.conj_mode = a.variant; r.part_energy = d_energy; r.y0 = d_y0;
+        {
+            i64 g = (i64)NROWBLK * lanes;
+            typedef KRowCorr<RS, RPC, 3> K3;
+            typedef KRowCorr<RS, RPC, 1> K1;
+            const i64 wave = (i64)be->num_sms * K3::MINB;      // resident CTAs: TMEM columns are per CTA
+            if (g > wave) g = wave;
+            if (nq == 3) be->template launch<K3>(dim3((unsigned)g, 1, 1), r);
+            else be->template launch<K1>(dim3((unsigned)g, 1, 1), r);
+        }
         ColParams c{};
         c.src = d_B; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.invN = 1.0 / (double)N; c.nch = 1; c.nq = nq; c.part_key = d_keycol;
         c.ntx = NCOLTILE; c.ny = lanes * nq;
         typedef KCol<CS, TS, SRC_CF32, COL_INV_ARGMAX> KCI;
         be->template launch<KCI>(pgrid<KCI>((i64)c.ntx * c.ny), c);
-        PeakTabParams pt{};
-        pt.part_key = d_keycol; pt.npart = nq * NCOLTILE; pt.N = N; pt.nq = nq; pt.L1 = L1; pt.N2 = N2;
-        pt.p0_out = d_p0; pt.rowph = d_rowph; pt.wk2 = d_wk2; pt.nsplit = 16;
-        be->template launch<KPeakTables>(dim3(pt.nsplit, lanes, 1), pt);
-        PeakSumParams ps{};
-        ps.P = d_P; ps.rowph = d_rowph; ps.wk2 = d_wk2; ps.N = N; ps.L1 = L1; ps.N2 = N2; ps.part = d_peakpart;
-        ps.nblk = NPEAKBLK;
-        be->template launch<KPeakSums<L1>>(dim3(NPEAKBLK, lanes, 1), ps);
+        PeakEvalParams pe{};
+        pe.part_key = d_keycol; pe.npart = nq * NCOLTILE; pe.B = d_B; pe.N = N; pe.nq = nq; pe.L1 = L1; pe.N2 = N2;
+        pe.p0_out = d_p0; pe.part = d_peakpart;
+        be->template launch<KPeakEval>(dim3(PEAK_NPTS, lanes, 1), pe);
         PeakFinParams pf{};
-        pf.part = d_peakpart; pf.nblk = NPEAKBLK; pf.part_energy = d_energy; pf.nen = NROWBLK; pf.y0 = d_y0;
+        pf.part = d_peakpart; pf.nblk = 1; pf.part_energy = d_energy; pf.nen = NROWBLK; pf.y0 = d_y0;
         pf.p0 = d_p0; pf.df = d_df; pf.sbin = d_sbin; pf.N = N; pf.nq = nq; pf.variant = a.variant; pf.ddof = a.ddof;
         pf.out = a.d_out;
         be->template launch<KPeakFinal>(dim3(1, lanes, 1), pf);
@@ -275,7 +270,6 @@ public:
         switch (what) {
         case 0: src = d_code; break;
         case 1: src = d_A + (size_t)lane * N; break;
-        case 2: src = d_P + (size_t)lane * N; break;
         case 3: src = d_B + (size_t)lane * nq * N; break;
         case 4: src = d_sums + (size_t)lane * 2; break;
         case 5: src = d_df + lane; break;

@@ -33,10 +33,9 @@ METRIC = "two-channel 1-s 5 MS/s records correlated per second"
 UNIT = "records/s"
 SURVEY_BYTES_PER_RECORD = 1.4e9  # 140*N bytes per channel, two channels
 # algorithmic bytes per lane (one channel of one record) and launch, in units of N bytes
-ALG_BYTES_N = {"mean": 4, "col_fwd_raw": 12, "row_fwd_argmax": 8, "row_fwd_mulcode": 24,
-               "row_inv_twist": 32, "col_inv_argmax": 24, "peak_sums": 8}
+ALG_BYTES_N = {"mean": 4, "col_fwd_raw": 12, "row_fwd_argmax": 8, "row_corr": 32, "col_inv_argmax": 24}
 LAUNCHES_PER_LANE = {"col_fwd_raw": 2}          # estimator pass + derotated pass
-ALG_TOTAL_N = sum(v * LAUNCHES_PER_LANE.get(k, 1) for k, v in ALG_BYTES_N.items())   # 124
+ALG_TOTAL_N = sum(v * LAUNCHES_PER_LANE.get(k, 1) for k, v in ALG_BYTES_N.items())   # 92
 
 
 def measured_peak():
