@@ -49,6 +49,11 @@ struct Backend {
     {
         if (stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
+        for (int s = 0; s < 2; s++) {
+            if (ev_copied[s]) cudaEventDestroy(ev_copied[s]);
+            if (ev_consumed[s]) cudaEventDestroy(ev_consumed[s]);
+            ev_copied[s] = ev_consumed[s] = nullptr;
+        }
         stream = copy_stream = nullptr;
     }
     void use() { cudaSetDevice(device); }
@@ -63,6 +68,26 @@ struct Backend {
     void h2d(void* d, const void* h, size_t bytes) { note(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream)); }
     void d2h(void* h, const void* d, size_t bytes) { note(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, stream)); }
     void sync() { note(cudaStreamSynchronize(stream)); }
+    // Double-buffered input staging: host->device copies run on copy_stream and overlap the kernels of
+    // the previous chunk on `stream`; slot s is reused only after the kernels that read it have finished.
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    bool slot_used[2] = {false, false};
+    void stage_copy(int slot, void* d, const void* h, size_t bytes)
+    {
+        if (!ev_copied[slot]) {
+            note(cudaEventCreateWithFlags(&ev_copied[slot], cudaEventDisableTiming));
+            note(cudaEventCreateWithFlags(&ev_consumed[slot], cudaEventDisableTiming));
+        }
+        if (slot_used[slot]) note(cudaStreamWaitEvent(copy_stream, ev_consumed[slot], 0));
+        note(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, copy_stream));
+        note(cudaEventRecord(ev_copied[slot], copy_stream));
+        note(cudaStreamWaitEvent(stream, ev_copied[slot], 0));
+    }
+    void stage_release(int slot)
+    {
+        note(cudaEventRecord(ev_consumed[slot], stream));
+        slot_used[slot] = true;
+    }
     // optional per-kernel CUDA-event profiling (bench.py roofline leg): one event pair per launch
     struct ProfSlot { const char* name; double ms; long count; };
     bool profiling = false;

@@ -32,9 +32,10 @@ constexpr int split_kd(int ns)
 }
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
-// seeds of a radix-R stage: w^1..w^(B-1), w^B, w^2B, ..., w^(R-B)
-template <int R> struct Seeds {
-    static constexpr int B = (R <= 5) ? R : ((R % 5 == 0) ? 5 : 4);
+// seeds of a radix-R stage: w^1..w^(B-1), w^B, w^2B, ..., w^(R-B).  FULL: every power comes from the
+// table (B = R), used where the table is small (root index <= 32 values): no products at all.
+template <int R, bool FULL = false> struct Seeds {
+    static constexpr int B = (FULL || R <= 5) ? R : ((R % 5 == 0) ? 5 : 4);
     static constexpr int NLOW = B - 1;                 // w^1..w^(B-1)
     static constexpr int NHIGH = R / B - 1;            // w^B..w^(R-B)
     static constexpr int N = NLOW + NHIGH;
@@ -56,7 +57,9 @@ template <int R0_, int R1_ = 1, int R2_ = 1> struct FFTSpec {
     static constexpr int SP0 = R1 * R2;           // stride of digit i0 (= butterflies in stage 0)
     // stage-0 twiddle tables: root index jb in [0, SP0)
     static constexpr int KD0 = split_kd(SP0), KH0 = SP0 / KD0;
-    static constexpr int NSEED0 = Seeds<R0>::N, NSEED1 = Seeds<R1>::N;
+    typedef Seeds<R0, false> SD0;          // stage-0 twiddles w = W_L^jb, jb in [0, SP0)
+    typedef Seeds<R1, false> SD1;                // middle-stage twiddles w = W_{R1 R2}^i2, i2 in [0, R2)
+    static constexpr int NSEED0 = SD0::N, NSEED1 = SD1::N;
     static constexpr int OFF_B0 = 0;
     static constexpr int OFF_A0 = OFF_B0 + (NSTAGE > 1 ? NSEED0 * KD0 : 0);
     // middle-stage twiddle table (3 stages only): root index i2 in [0, R2), R2 <= 32
@@ -72,7 +75,7 @@ template <class S> void fill_blob(float2* out)
     const double TWO_PI = 6.283185307179586476925287;
     if (S::NSTAGE > 1) {
         for (int row = 0; row < S::NSEED0; row++) {
-            const int m = Seeds<S::R0>::exponent(row);
+            const int m = S::SD0::exponent(row);
             for (int kl = 0; kl < S::KD0; kl++) {
                 double a = -TWO_PI * (double)((long long)m * kl) / (double)S::L;
                 out[S::OFF_B0 + row * S::KD0 + kl] = make_float2((float)cos(a), (float)sin(a));
@@ -86,7 +89,7 @@ template <class S> void fill_blob(float2* out)
     }
     if (S::NSTAGE == 3) {
         for (int row = 0; row < S::NSEED1; row++) {
-            const int m = Seeds<S::R1>::exponent(row);
+            const int m = S::SD1::exponent(row);
             for (int i2 = 0; i2 < S::R2; i2++) {
                 double a = -TWO_PI * (double)(m * i2) / (double)(S::R1 * S::R2);
                 out[S::OFF_B1 + row * S::R2 + i2] = make_float2((float)cos(a), (float)sin(a));
@@ -96,9 +99,8 @@ template <class S> void fill_blob(float2* out)
 }
 
 // Multiply outputs v[1..R-1] of a butterfly by w^m, the seeds read through `seed(row)`.
-template <int R, class SeedFn> HD void apply_powers(float2* v, SeedFn seed)
+template <int R, class SD, class SeedFn> HD void apply_powers(float2* v, SeedFn seed)
 {
-    typedef Seeds<R> SD;
     float2 lo[SD::NLOW > 0 ? SD::NLOW : 1];
 #pragma unroll
     for (int b = 1; b < SD::B; b++) {
@@ -144,7 +146,7 @@ template <class S, class Acc> HD void dif_stage0(int j, float2* v, const float2*
         if (S::NSTAGE > 1) {
             const float2* tb = tw + S::OFF_B0 + jb % S::KD0;
             const float2* ta = tw + S::OFF_A0 + jb / S::KD0;
-            apply_powers<R>(vb, [&](int row) {
+            apply_powers<R, typename S::SD0>(vb, [&](int row) {
                 float2 w = tb[row * S::KD0];
                 if (S::KH0 > 1) w = cmul(w, ta[row * S::KH0]);
                 return w;
@@ -170,7 +172,7 @@ template <class S, class Acc> HD void dif_stage_mid(int j, float2* v, const floa
         for (int m = 0; m < R; m++) vb[m] = p[m * S::R2 * Acc::unit()];
         Bfly<R>::run(vb);
         const float2* tb = tw + S::OFF_B1 + i2;
-        apply_powers<R>(vb, [&](int row) { return tb[row * S::R2]; });
+        apply_powers<R, typename S::SD1>(vb, [&](int row) { return tb[row * S::R2]; });
 #pragma unroll
         for (int m = 0; m < R; m++) p[m * S::R2 * Acc::unit()] = vb[m];
     }

@@ -48,7 +48,9 @@ struct ColParams {
     u64* part_key;         // [y][ntx]
 };
 
-template <class S, int TS, int SRC, int MODE, int OP = 0> struct KCol {
+// N2C / NCH: row length and channel count as compile-time constants (0 = take them from Params), so that
+// the strided global accesses of a column become immediate offsets from one base register.
+template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH = 0> struct KCol {
     typedef ColParams Params;
     static const char* name()
     {
@@ -82,6 +84,8 @@ template <class S, int TS, int SRC, int MODE, int OP = 0> struct KCol {
     {
         return (ph == NCOMP - 1 && MODE == COL_INV_ARGMAX) ? SYNC_MAXKEY : SYNC_BARRIER;
     }
+    static HD int n2of(const Params& p) { return N2C > 0 ? N2C : n2of(p); }
+    static HD int nchof(const Params& p) { return NCH > 0 ? NCH : nchof(p); }
     static HD int niter(const Params& p, int bx, int gdim)
     {
         const i64 total = (i64)p.ntx * p.ny;
@@ -113,13 +117,13 @@ template <class S, int TS, int SRC, int MODE, int OP = 0> struct KCol {
     {
         const int col = wk.x * TS + s;
         if (SRC == SRC_RAW) {
-            const i64 lane = (i64)wk.y * p.nch + col % p.nch;
+            const i64 lane = (i64)wk.y * nchof(p) + col % nchof(p);
             float mx = 0.f, my = 0.f;
             if (p.sub_mean) {
                 mx = (float)(p.sums[lane * 2] * p.invN);
                 my = (float)(p.sums[lane * 2 + 1] * p.invN);
             }
-            const i64 rowlen = (i64)p.nch * p.N2;
+            const i64 rowlen = (i64)nchof(p) * n2of(p);
             const i64 rbase = p.rec_offset ? p.rec_offset[wk.y] : (i64)wk.y * p.rec_stride;
             const short2* gsrc = reinterpret_cast<const short2*>(p.src) + rbase + (i64)j * rowlen + col;
             const i64 bstride = (i64)S::NTS * rowlen, mstride = (i64)S::SP0 * rowlen;
@@ -133,8 +137,8 @@ template <class S, int TS, int SRC, int MODE, int OP = 0> struct KCol {
                     r.v[b * S::R0 + m] = pre_op(x, OP == 1 ? lr[S::NTS * b + m * S::SP0] : x);
                 }
         } else if (SRC == SRC_CF32) {
-            const float2* gsrc = reinterpret_cast<const float2*>(p.src) + (i64)wk.y * p.N + (i64)j * p.N2 + col;
-            const i64 bstride = (i64)S::NTS * p.N2, mstride = (i64)S::SP0 * p.N2;
+            const float2* gsrc = reinterpret_cast<const float2*>(p.src) + (i64)wk.y * p.N + (i64)j * n2of(p) + col;
+            const i64 bstride = (i64)S::NTS * n2of(p), mstride = (i64)S::SP0 * n2of(p);
 #pragma unroll
             for (int b = 0; b < NB0; b++)
 #pragma unroll
@@ -148,7 +152,7 @@ template <class S, int TS, int SRC, int MODE, int OP = 0> struct KCol {
             for (int b = 0; b < NB0; b++)
 #pragma unroll
                 for (int m = 0; m < S::R0; m++) {
-                    const i64 n = (i64)(j + S::NTS * b + m * S::SP0) * p.N2 + col;
+                    const i64 n = (i64)(j + S::NTS * b + m * S::SP0) * n2of(p) + col;
                     const i64 chip = n / p.rep;
                     r.v[b * S::R0 + m] = p.qpsk ? make_float2((float)bits[2 * chip] - p.code_mean.x,
                                                               (float)bits[2 * chip + 1] - p.code_mean.y)
@@ -160,40 +164,46 @@ template <class S, int TS, int SRC, int MODE, int OP = 0> struct KCol {
     static HD void epilogue(const Params& p, const Work& wk, int s, int j, Regs& r, const float2* g)
     {
         const int col = wk.x * TS + s;
-        const int ch = (SRC == SRC_RAW) ? col % p.nch : 0;
-        const int n2 = (SRC == SRC_RAW) ? col / p.nch : col;
+        const int ch = (SRC == SRC_RAW) ? col % nchof(p) : 0;
+        const int n2 = (SRC == SRC_RAW) ? col / nchof(p) : col;
         if (MODE == COL_FWD) {
-            const i64 lane = (SRC == SRC_RAW) ? (i64)wk.y * p.nch + ch : (i64)wk.y;
+            const i64 lane = (SRC == SRC_RAW) ? (i64)wk.y * nchof(p) + ch : (i64)wk.y;
             float2* d = p.dst + lane * p.N + n2;
             float2 base[NBL];
 #pragma unroll
             for (int b = 0; b < NBL; b++) {
                 const int jb = j + S::NTS * b;
                 base[b] = cis_cycles(-(double)((i64)n2 * jb) * p.invN);
-                if (SRC == SRC_RAW && OP == 1) base[b] = cmul(base[b], p.lcol[lane * p.N2 + n2]);
+                if (SRC == SRC_RAW && OP == 1) base[b] = cmul(base[b], p.lcol[lane * n2of(p) + n2]);
             }
-            const i64 bstr = (i64)S::NTS * p.N2, mstr = (i64)S::NSLAST * p.N2;
-            float2* dj = d + (i64)j * p.N2;
+            const i64 bstr = (i64)S::NTS * n2of(p), mstr = (i64)S::NSLAST * n2of(p);
+            float2* dj = d + (i64)j * n2of(p);
             last_stage_visit<S>(j, r.v, [&](int, float2 x, int b, int m) {
                 dj[b * bstr + m * mstr] = cmul(x, cmul(base[b], g[m * TS + s]));
             });
         } else if (MODE == COL_INV_STORE) {
-            float2* dj = p.dst + (i64)wk.y * p.N + n2 + (i64)j * p.N2;
-            const i64 bstr = (i64)S::NTS * p.N2, mstr = (i64)S::NSLAST * p.N2;
+            float2* dj = p.dst + (i64)wk.y * p.N + n2 + (i64)j * n2of(p);
+            const i64 bstr = (i64)S::NTS * n2of(p), mstr = (i64)S::NSLAST * n2of(p);
             last_stage_visit<S>(j, r.v, [&](int, float2 x, int b, int m) { dj[b * bstr + m * mstr] = cswap(x); });
         } else {  // COL_INV_ARGMAX: outputs are visited in increasing index, so '>' keeps the first maximum
             const int q = wk.y % p.nq;
             float bestv = -1.f;
-            unsigned besti = 0;
-            const unsigned i0 = (unsigned)p.nq * (unsigned)n2 + (unsigned)q;
-            const unsigned istep = (unsigned)p.nq * (unsigned)p.N2;
-            last_stage_visit<S>(j, r.v, [&](int o, float2 x, int, int) {
+            int bestc = 0;                  // output index = j + bestc; b and m are compile-time after unrolling
+            last_stage_visit<S>(j, r.v, [&](int, float2 x, int b, int m) {
                 const float v = cnorm(x);
-                const unsigned idx = i0 + istep * (unsigned)o;
-                if (v > bestv || (NBL > 1 && v == bestv && idx < besti)) { bestv = v; besti = idx; }
+                const int c = S::NTS * b + m * S::NSLAST;
+                if (v > bestv || (NBL > 1 && v == bestv && c < bestc)) { bestv = v; bestc = c; }
             });
+            const unsigned besti = (unsigned)p.nq * (unsigned)n2 + (unsigned)q +
+                                   (unsigned)p.nq * (unsigned)n2of(p) * (unsigned)(j + bestc);
             r.key = make_key(bestv, besti);
         }
+    }
+
+    static HD void prologue(const Params& p, int tid, unsigned char* smem)
+    {
+        float2* sm = reinterpret_cast<float2*>(smem);
+        for (int i = tid; i < S::BLOB; i += NT) sm[i] = p.blob[i];
     }
 
     template <int PH>
@@ -213,20 +223,18 @@ template <class S, int TS, int SRC, int MODE, int OP = 0> struct KCol {
         if (PH == 0) {
             r.key = 0;
             r.dsum[0] = 0.0;
-            if (it == 0 && S::NSTAGE == 3)          // only the middle stage reads the shared copy
-                for (int i = tid; i < S::BLOB; i += NTA) sm[i] = p.blob[i];
             if (MODE == COL_FWD) {
                 for (int t = tid; t < NG; t += NTA) {
                     const int s2 = t % TS, m = t / TS;
                     const int col2 = wk.x * TS + s2;
-                    const i64 n2b = (SRC == SRC_RAW) ? col2 / p.nch : col2;
+                    const i64 n2b = (SRC == SRC_RAW) ? col2 / nchof(p) : col2;
                     gtab[m * TS + s2] = cis_cycles(-(double)(n2b * S::NSLAST * m) * p.invN);
                 }
             }
         }
         if (PH == (S::NSTAGE == 1 ? 1 : 0)) {
             load0(p, wk, s, j, r);
-            dif_stage0<S>(j, r.v, p.blob, acc);      // stage-0 seeds from global/L1 (shared copy not yet valid)
+            dif_stage0<S>(j, r.v, sm, acc);
             if (S::NSTAGE == 1) epilogue(p, wk, s, j, r, gtab);
         }
         if (S::NSTAGE == 3 && PH == 1) dif_stage_mid<S>(j, r.v, sm, acc);

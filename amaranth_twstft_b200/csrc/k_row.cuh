@@ -199,6 +199,12 @@ template <class S, int RPC, int MODE> struct KRow {
         }
     }
 
+    static HD void prologue(const Params& p, int tid, unsigned char* smem)
+    {
+        float2* sm = reinterpret_cast<float2*>(smem);
+        for (int i = tid; i < S::BLOB; i += NT) sm[i] = p.blob[i];
+    }
+
     template <int PH>
     static HD void phase(const Params& p, const Blk& blk, int tid, Regs& r, unsigned char* smem, int it, int nit)
     {
@@ -216,8 +222,6 @@ template <class S, int RPC, int MODE> struct KRow {
         if (PH == 0) {
             r.key = 0;
             r.dsum[0] = 0.0;
-            if (it == 0 && S::NSTAGE == 3)          // only the middle stage reads the shared copy
-                for (int i = tid; i < S::BLOB; i += NTA) sm[i] = p.blob[i];
             if (MODE == ROW_INV_TWIST) {
                 for (int t = tid; t < NG; t += NTA) {
                     const int rl2 = t / S::RLAST, m = t % S::RLAST;
@@ -228,8 +232,7 @@ template <class S, int RPC, int MODE> struct KRow {
         }
         if (PH == (S::NSTAGE == 1 ? 1 : 0)) {
             load0(p, wk, rl, j, r);
-            dif_stage0<S>(j, r.v, p.blob, acc);      // stage-0 seeds straight from global/L1: the shared copy
-                                                     // of the blob is only valid after the first barrier
+            dif_stage0<S>(j, r.v, sm, acc);
             if (S::NSTAGE == 1) epilogue(p, wk, rl, j, r, gtab);
         }
         if (S::NSTAGE == 3 && PH == 1) dif_stage_mid<S>(j, r.v, sm, acc);

@@ -154,6 +154,13 @@ template <class S, int RPC, int NQ> struct KRowCorr {
 #endif
     }
 
+    static HD void prologue(const Params& p, int tid, unsigned char* smem)
+    {
+        float2* sm = reinterpret_cast<float2*>(smem);
+        for (int i = tid; i < S::BLOB; i += NT) sm[i] = p.blob[i];
+        for (int i = tid; i < NQ * S::R0; i += NT) sm[OFF_QC + i] = p.qconst[i];
+    }
+
     template <int PH>
     static HD void phase(const Params& p, const Blk& blk, int tid, Regs& r, unsigned char* smem, int it, int nit)
     {
@@ -170,10 +177,6 @@ template <class S, int RPC, int NQ> struct KRowCorr {
             r.key = 0;
             r.dsum[0] = 0.0;
             if (active) {
-                if (it == 0) {
-                    for (int i = tid; i < S::BLOB; i += NTA) sm[i] = p.blob[i];
-                    for (int i = tid; i < NQ * S::R0; i += NTA) sm[OFF_QC + i] = p.qconst[i];
-                }
                 for (int t = tid; t < NG; t += NTA) {      // conjugate four-step twiddle steps of this item's rows
                     const int rl2 = t / S::RLAST, m = t % S::RLAST;
                     const i64 row2 = (i64)wk.rowblk * RPC + rl2;
@@ -184,7 +187,7 @@ template <class S, int RPC, int NQ> struct KRowCorr {
                 for (int b = 0; b < NB0; b++)
 #pragma unroll
                     for (int m = 0; m < S::R0; m++) r.v[b * S::R0 + m] = xj[S::NTS * b + m * S::SP0];
-                dif_stage0<S>(j, r.v, p.blob, acc);
+                dif_stage0<S>(j, r.v, sm, acc);
             }
         }
         if (F > 0 && ST == 0) {

@@ -79,11 +79,20 @@ __device__ __forceinline__ void run_phases(const typename K::Params& p, const Bl
 template <class K, class = void> struct TmemCols { static constexpr int value = 0; };
 template <class K> struct TmemCols<K, decltype((void)K::TMEM_COLS)> { static constexpr int value = K::TMEM_COLS; };
 
+// Kernels with per-CTA constant tables provide  static void prologue(p, tid, smem): it runs once per CTA,
+// followed by a block barrier, before the first work item.
+template <class K, class = void> struct HasPrologue { static constexpr bool value = false; };
+template <class K> struct HasPrologue<K, decltype((void)&K::prologue)> { static constexpr bool value = true; };
+
 template <class K> __global__ void __launch_bounds__(K::NT, K::MINB) kernel_entry(const typename K::Params p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     typename K::Regs r;
     Blk b{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z, (int)gridDim.x};
+    if constexpr (HasPrologue<K>::value) {
+        K::prologue(p, (int)threadIdx.x, smem);
+        __syncthreads();
+    }
     constexpr int TC = TmemCols<K>::value;
     if constexpr (TC > 0) {
         __shared__ unsigned tmem_slot;

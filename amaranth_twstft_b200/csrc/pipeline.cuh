@@ -55,11 +55,12 @@ public:
     virtual int debug_fetch(int what, int lane, void* host_out, size_t bytes) = 0;
 };
 
-template <class CS, class RS, int RPC, int TS> class Pipe : public IPipe {
+// TS: column-tile width of the forward (raw / code) column passes, TSI: of the inverse column pass
+template <class CS, class RS, int RPC, int TS, int TSI = TS> class Pipe : public IPipe {
 public:
     static constexpr i64 N = (i64)CS::L * RS::L;
     static constexpr int L1 = CS::L, N2 = RS::L;
-    static_assert(N2 % TS == 0 && (2 * N2) % TS == 0, "column tile must divide the row length");
+    static_assert(N2 % TS == 0 && (2 * N2) % TS == 0 && N2 % TSI == 0, "column tile must divide the row length");
     static_assert(L1 % RPC == 0, "rows per CTA must divide the column length");
     static_assert(N2 % 2 == 0, "negative-frequency split needs an even row length");
 
@@ -74,6 +75,7 @@ public:
     float2 *d_y0 = nullptr, *d_lrow = nullptr, *d_lcol = nullptr;
     static constexpr int NROWBLK = L1 / RPC;
     static constexpr int NCOLTILE = N2 / TS;
+    static constexpr int NCOLTILE_I = N2 / TSI;
 
     ~Pipe() override
     {
@@ -136,7 +138,7 @@ public:
         d_df = dalloc<double>(lanes);
         d_peakpart = dalloc<double>((size_t)lanes * 2 * PEAK_NPTS);
         d_keyrow = dalloc<u64>((size_t)lanes * NROWBLK);
-        d_keycol = dalloc<u64>((size_t)lanes * nq * NCOLTILE);
+        d_keycol = dalloc<u64>((size_t)lanes * nq * NCOLTILE_I);
         d_sbin = dalloc<i64>(lanes);
         d_p0 = dalloc<i64>(lanes);
         d_y0 = dalloc<float2>(lanes);
@@ -150,7 +152,7 @@ public:
         ColParams c{};
         c.src = d_bits; c.dst = d_A; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.invN = 1.0 / (double)N; c.nch = 1;
         c.rep = rep; c.qpsk = qpsk; c.code_mean = mean; c.nq = 1; c.ntx = NCOLTILE; c.ny = 1;
-        typedef KCol<CS, TS, SRC_BITS, COL_FWD> KC;
+        typedef KCol<CS, TS, SRC_BITS, COL_FWD, 0, N2, 1> KC;
         be->template launch<KC>(pgrid<KC>(NCOLTILE), c);
         RowParams r{};
         r.src = d_A; r.dst = d_code; r.blob = d_blob_r; r.N = N; r.N1 = L1; r.invN = 1.0 / (double)N; r.invM = 1.0 / ((double)nq * (double)N); r.nq = 1; r.nblk = NROWBLK;
@@ -180,8 +182,13 @@ public:
         c.sub_mean = sub_mean; c.sums = d_sums; c.lrow = d_lrow; c.lcol = d_lcol;
         c.rec_stride = a.rec_stride; c.rec_offset = a.d_rec_offset; c.nq = 1;
         c.ntx = NCOLTILE * a.nch; c.ny = a.nrec;
-        typedef KCol<CS, TS, SRC_RAW, COL_FWD, OP> KC;
-        be->template launch<KC>(pgrid<KC>((i64)c.ntx * c.ny), c);
+        if (a.nch == 2) {
+            typedef KCol<CS, TS, SRC_RAW, COL_FWD, OP, N2, 2> KC;
+            be->template launch<KC>(pgrid<KC>((i64)c.ntx * c.ny), c);
+        } else {
+            typedef KCol<CS, TS, SRC_RAW, COL_FWD, OP, N2, 1> KC;
+            be->template launch<KC>(pgrid<KC>((i64)c.ntx * c.ny), c);
+        }
     }
 
     void df_final(const RunArgs& a, const EstimatorCfg* e)
@@ -248,11 +255,11 @@ public:
         }
         ColParams c{};
         c.src = d_B; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.invN = 1.0 / (double)N; c.nch = 1; c.nq = nq; c.part_key = d_keycol;
-        c.ntx = NCOLTILE; c.ny = lanes * nq;
-        typedef KCol<CS, TS, SRC_CF32, COL_INV_ARGMAX> KCI;
+        c.ntx = NCOLTILE_I; c.ny = lanes * nq;
+        typedef KCol<CS, TSI, SRC_CF32, COL_INV_ARGMAX, 0, N2, 1> KCI;
         be->template launch<KCI>(pgrid<KCI>((i64)c.ntx * c.ny), c);
         PeakEvalParams pe{};
-        pe.part_key = d_keycol; pe.npart = nq * NCOLTILE; pe.B = d_B; pe.N = N; pe.nq = nq; pe.L1 = L1; pe.N2 = N2;
+        pe.part_key = d_keycol; pe.npart = nq * NCOLTILE_I; pe.B = d_B; pe.N = N; pe.nq = nq; pe.L1 = L1; pe.N2 = N2;
         pe.p0_out = d_p0; pe.part = d_peakpart;
         be->template launch<KPeakEval>(dim3(PEAK_NPTS, lanes, 1), pe);
         PeakFinParams pf{};
@@ -289,7 +296,7 @@ inline IPipe* make_pipe(i64 n)
     typedef FFTSpec<20, 20, 20> R8000;
     typedef FFTSpec<20, 20> R400;
     switch (n) {
-    case 5000000: return new Pipe<FFTSpec<25, 25>, R8000, 1, 16>();    // 1-s window, 2.5 Mchip/s code
+    case 5000000: return new Pipe<FFTSpec<25, 25>, R8000, 1, 16, 8>();    // 1-s window, 2.5 Mchip/s code
     case 1000000: return new Pipe<FFTSpec<5, 25>, R8000, 1, 16>();     // 500 kchip codes
     case 200000: return new Pipe<FFTSpec<25>, R8000, 1, 64>();         // 100 kchip/s code windows
     case 250000: return new Pipe<FFTSpec<25, 25>, R400, 5, 16>();      // test size (same column kernel as 5e6)

@@ -19,9 +19,10 @@ struct twstft_plan {
     int nq = 3;
     int max_lanes = 0;
     bool have_code = false;
-    short2* d_raw = nullptr;       // staging for host inputs: max_batch records
+    short2* d_raw = nullptr;       // staging for host inputs: two slots of max_batch records
     size_t raw_elems_per_rec = 0;
     Result* d_res = nullptr;
+    size_t res_cap = 0;            // rows d_res can hold
     double* d_dfin = nullptr;
     i64* d_off = nullptr;
     unsigned char* d_bits = nullptr;
@@ -103,6 +104,7 @@ int twstft_plan_create(const twstft_config* cfg, twstft_plan** out)
     const i64 N = cfg->nsamples;
     p->raw_elems_per_rec = (size_t)N * p->nch;
     p->d_res = (Result*)p->be.alloc(sizeof(Result) * p->max_lanes);
+    p->res_cap = (size_t)p->max_lanes;
     p->d_dfin = (double*)p->be.alloc(sizeof(double) * p->max_lanes);
     p->d_off = (i64*)p->be.alloc(sizeof(i64) * cfg->max_batch);
     // frequency axis of the estimator: length = window length
@@ -256,7 +258,7 @@ int twstft_prn_generate(int device_id, int bitlen, uint32_t taps_a, uint32_t tap
 static int ensure_raw(twstft_plan* p)
 {
     if (p->d_raw) return 0;
-    p->d_raw = (short2*)p->be.alloc(sizeof(short2) * p->raw_elems_per_rec * p->cfg.max_batch);
+    p->d_raw = (short2*)p->be.alloc(sizeof(short2) * p->raw_elems_per_rec * p->cfg.max_batch * 2);
     return p->be.ok() ? 0 : -1;
 }
 
@@ -287,20 +289,46 @@ int twstft_process_device(twstft_plan* p, const int16_t* iq_dev, size_t nrecords
     return process_dev(p, reinterpret_cast<const short2*>(iq_dev), nrecords, results);
 }
 
+static int ensure_results(twstft_plan* p, size_t rows)
+{
+    if (p->res_cap >= rows) return 0;
+    p->be.sync();
+    p->be.free(p->d_res);
+    p->d_res = (Result*)p->be.alloc(sizeof(Result) * rows);
+    p->res_cap = rows;
+    return p->be.ok() ? 0 : -1;
+}
+
+// Host records: the input is streamed in chunks through two staging slots so that the PCIe copy of
+// chunk c+1 overlaps the kernels of chunk c; one result copy at the end.
 int twstft_process(twstft_plan* p, const int16_t* iq, size_t nrecords, twstft_result* results)
 {
     if (!p || !p->pipe || !iq || !results) return TWSTFT_E_ARG;
     if (!p->have_code) return fail(p, TWSTFT_E_NOCODE, "no PRN code installed (twstft_set_code / twstft_gen_code)");
+    if (nrecords == 0) return TWSTFT_OK;
     p->be.use();
-    if (ensure_raw(p) != 0) return fail(p, TWSTFT_E_NOMEM, "device allocation failed");
-    const int B = p->cfg.max_batch;
+    if (ensure_raw(p) != 0 || ensure_results(p, nrecords * p->nch) != 0)
+        return fail(p, TWSTFT_E_NOMEM, "device allocation failed");
+    const size_t B = (size_t)p->cfg.max_batch;
+    size_t chunk = B / 4;
+    if (chunk < 1) chunk = 1;
     const short2* h = reinterpret_cast<const short2*>(iq);
-    for (size_t r0 = 0; r0 < nrecords; r0 += B) {
-        const size_t nb = (nrecords - r0) < (size_t)B ? (nrecords - r0) : B;
-        p->be.h2d(p->d_raw, h + r0 * p->raw_elems_per_rec, sizeof(short2) * p->raw_elems_per_rec * nb);
-        int rc = process_dev(p, p->d_raw, nb, results + r0 * p->nch);
-        if (rc != 0) return rc;
+    int slot = 0;
+    for (size_t r0 = 0; r0 < nrecords; r0 += chunk, slot ^= 1) {
+        const size_t nb = (nrecords - r0) < chunk ? (nrecords - r0) : chunk;
+        short2* d = p->d_raw + (size_t)slot * B * p->raw_elems_per_rec;
+        p->be.stage_copy(slot, d, h + r0 * p->raw_elems_per_rec, sizeof(short2) * p->raw_elems_per_rec * nb);
+        RunArgs a{};
+        a.d_raw = d; a.nrec = (int)nb; a.nch = p->nch; a.rec_stride = (i64)p->raw_elems_per_rec; a.d_rec_offset = nullptr;
+        a.estimate = 1; a.variant = p->cfg.variant; a.ddof = p->cfg.ddof; a.fs = p->cfg.fs;
+        a.d_out = p->d_res + r0 * p->nch;
+        if (p->pipe->estimate(a, p->est) != 0 || p->pipe->correlate(a) != 0)
+            return fail(p, TWSTFT_E_CUDA, p->be.err_string());
+        p->be.stage_release(slot);
     }
+    p->be.d2h(results, p->d_res, sizeof(Result) * nrecords * p->nch);
+    p->be.sync();
+    if (!p->be.ok()) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
     return TWSTFT_OK;
 }
 

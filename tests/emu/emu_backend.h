@@ -53,6 +53,8 @@ struct Backend {
     void h2d(void* d, const void* h, size_t bytes) { memcpy(d, h, bytes); }
     void d2h(void* h, const void* d, size_t bytes) { memcpy(h, d, bytes); }
     void sync() {}
+    void stage_copy(int, void* d, const void* h, size_t bytes) { memcpy(d, h, bytes); }
+    void stage_release(int) {}
     struct ProfSlot { const char* name; double ms; long count; };
     bool profiling = false;
     std::vector<ProfSlot> prof;
@@ -67,6 +69,8 @@ struct Backend {
             for (unsigned y = 0; y < grid.y; y++)
                 for (unsigned x = 0; x < grid.x; x++) {
                     Blk b{(int)x, (int)y, (int)z, (int)grid.x};
+                    if constexpr (HasPrologue<K>::value)
+                        for (int tid = 0; tid < K::NT; tid++) K::prologue(p, tid, smem.data());
                     if constexpr (K::PERSISTENT) {
                         const int nit = K::niter(p, (int)x, (int)grid.x);
                         for (int it = 0; it < nit; it++) EmuPhases<K, 0>::run(p, b, regs, smem.data(), it, nit);

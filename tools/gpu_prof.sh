@@ -2,8 +2,8 @@
 # ncu: launch list of one bench step + full-set capture of one launch of every hot kernel
 mkdir -p gpurun_out
 R=${1:-4}
-# launches: 3 (code) + 11 (warm-up pass) = 14 skipped
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 14 -c 11 --csv --log-file gpurun_out/launches.csv python tools/prof_run.py $R 1 > gpurun_out/prof_launch.log 2>&1
-timeout 1500 ncu --set full --clock-control none --import-source on -s 14 -c 11 -f -o gpurun_out/prof_full python tools/prof_run.py $R 1 > gpurun_out/prof_full.log 2>&1
+# launches: 3 (code) + 9 (warm-up pass) = 12 skipped
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 12 -c 9 --csv --log-file gpurun_out/launches.csv python tools/prof_run.py $R 1 > gpurun_out/prof_launch.log 2>&1
+timeout 1500 ncu --set full --clock-control none --import-source on -s 12 -c 9 -f -o gpurun_out/prof_full python tools/prof_run.py $R 1 > gpurun_out/prof_full.log 2>&1
 ls -la gpurun_out/
 tail -3 gpurun_out/prof_full.log
