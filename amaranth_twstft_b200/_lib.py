@@ -22,7 +22,7 @@ EXPORTS = [
     "twstft_process_device", "twstft_process_windows", "twstft_estimate_carrier", "twstft_host_alloc",
     "twstft_host_free", "twstft_device_alloc", "twstft_device_free", "twstft_copy_to_device",
     "twstft_copy_to_host", "twstft_synchronize", "twstft_kernel_launches", "twstft_debug_fetch",
-    "twstft_window_bins", "twstft_timer_start", "twstft_timer_stop", "twstft_profile_enable", "twstft_profile_read",
+    "twstft_window_bins", "twstft_doppler_bank", "twstft_search_df", "twstft_timer_start", "twstft_timer_stop", "twstft_profile_enable", "twstft_profile_read",
 ]
 
 
@@ -42,6 +42,9 @@ RESULT_FIELDS = ["indice", "correction", "xval_re", "xval_im", "xvalm1_re", "xva
 
 class Result(C.Structure):
     _fields_ = [(n, C.c_double) for n in RESULT_FIELDS]
+
+
+BANK_FIELDS = ["b0", "prnsig", "metric", "status"]
 
 
 class LibraryMissing(RuntimeError):
@@ -77,6 +80,8 @@ def load(path=None):
     lib.twstft_process_device.argtypes = [P, P, C.c_size_t, P]
     lib.twstft_process_windows.argtypes = [P, P, C.c_int, C.c_size_t, P, P, C.c_size_t, P]
     lib.twstft_estimate_carrier.argtypes = [P, P, C.c_int, C.c_size_t, P, P]
+    lib.twstft_doppler_bank.argtypes = [P, P, C.c_int, C.c_size_t, C.c_int64, P, C.c_size_t, C.c_int, P]
+    lib.twstft_search_df.argtypes = [P, P, C.c_int, C.c_size_t, C.c_int64, C.c_double, P, P, P]
     lib.twstft_host_alloc.argtypes = [C.c_size_t]
     lib.twstft_host_alloc.restype = P
     lib.twstft_host_free.argtypes = [P]

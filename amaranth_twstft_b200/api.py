@@ -4,6 +4,9 @@ Reference seams mirrored here (paths relative to the reference root):
   Correlator.process          record loop of processing/Octave/godual_ranging.m:75-102
   Correlator.process_windows  processing(d,k,df) of acquisition/claudio_aligned_code_lo_separate.m:24-77
   Correlator.estimate_carrier godual_ranging.m:14-15
+  Correlator.doppler_bank     per-bin body of search_df over a grid of offsets (cross-ambiguity search),
+                              acquisition/claudio_aligned_code_re_separate.m:33-42
+  Correlator.search_df        k=search_df(d,k,df_threshold), claudio_aligned_code_re_separate.m:26-46
   Correlator.gen_code/set_code  amaranth_twstft/common.py:59-73 / godual_ranging.m:62-66
 Results come back as a numpy structured array whose field names are the reference's .mat
 variable names (indice, correction, SNRr, SNRi, df, puissance, puissancecode, puissancenoise, xval*).
@@ -15,6 +18,7 @@ import numpy as np
 from . import _lib
 
 RESULT_DTYPE = np.dtype([(n, np.float64) for n in _lib.RESULT_FIELDS])
+BANK_DTYPE = np.dtype([(n, np.float64) for n in _lib.BANK_FIELDS])
 
 
 class TwstftError(RuntimeError):
@@ -149,6 +153,28 @@ class Correlator:
         self._check(self.lib.twstft_estimate_carrier(self._plan, iq.ctypes.data, 0, nrec, df.ctypes.data,
                                                      bins.ctypes.data), "twstft_estimate_carrier")
         return df, bins
+
+    def doppler_bank(self, iq, dfs, offset=0, sub_mean=True):
+        """Correlate the window of N sample instants at `offset` of the host buffer `iq` at 1x for every carrier
+        offset in dfs; returns a structured array (nbins, nch) with b0, prnsig, metric, status."""
+        iq = np.ascontiguousarray(iq, dtype=np.int16)
+        dfs = np.ascontiguousarray(dfs, dtype=np.float64)
+        out = np.zeros((len(dfs), self.nch), dtype=BANK_DTYPE)
+        self._check(self.lib.twstft_doppler_bank(self._plan, iq.ctypes.data, 0, iq.size // (2 * self.nch), int(offset),
+                                                 dfs.ctypes.data, len(dfs), int(sub_mean), out.ctypes.data),
+                    "twstft_doppler_bank")
+        return out
+
+    def search_df(self, iq, df_threshold=20.0, offset=0):
+        """k=search_df(d,k,df_threshold): returns (kbon[nch] 1-based shifted-axis index or 0, df[nch], ncand[nch])."""
+        iq = np.ascontiguousarray(iq, dtype=np.int16)
+        kbon = np.zeros(self.nch, dtype=np.int64)
+        df = np.zeros(self.nch)
+        ncand = np.zeros(self.nch, dtype=np.int32)
+        self._check(self.lib.twstft_search_df(self._plan, iq.ctypes.data, 0, iq.size // (2 * self.nch), int(offset),
+                                              float(df_threshold), kbon.ctypes.data, df.ctypes.data, ncand.ctypes.data),
+                    "twstft_search_df")
+        return kbon, df, ncand
 
     # ------------------------------------------------------------------ timing (CUDA events on the plan's stream)
     def timer_start(self):

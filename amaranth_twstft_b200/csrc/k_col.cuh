@@ -18,7 +18,7 @@
 namespace twstft {
 
 enum ColSrc { SRC_RAW = 0, SRC_CF32 = 1, SRC_BITS = 2 };
-enum ColMode { COL_FWD = 0, COL_INV_ARGMAX = 1, COL_INV_STORE = 2 };
+enum ColMode { COL_FWD = 0, COL_INV_ARGMAX = 1, COL_INV_STORE = 2, COL_INV_ARGMAX_STATS = 3 };
 
 struct ColParams {
     const void* src;
@@ -46,6 +46,7 @@ struct ColParams {
     // COL_INV_*
     int nq;
     u64* part_key;         // [y][ntx]
+    double* part_stat;     // COL_INV_ARGMAX_STATS: [y][ntx][2]  sum|z|, sum|z|^2 of the tile
 };
 
 // N2C / NCH: row length and channel count as compile-time constants (0 = take them from Params), so that
@@ -54,7 +55,8 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
     typedef ColParams Params;
     static const char* name()
     {
-        return MODE == COL_INV_ARGMAX ? "col_inv_argmax" : MODE == COL_INV_STORE ? "col_inv_store"
+        return MODE == COL_INV_ARGMAX ? "col_inv_argmax" : MODE == COL_INV_ARGMAX_STATS ? "col_inv_argmax_stats"
+             : MODE == COL_INV_STORE ? "col_inv_store"
              : SRC == SRC_RAW ? "col_fwd_raw" : SRC == SRC_BITS ? "col_fwd_bits" : "col_fwd_cf32";
     }
     static constexpr bool PERSISTENT = true;
@@ -66,9 +68,10 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
     static constexpr int OFF_G = S::BLOB_PAD;
     static constexpr int OFF_DATA = OFF_G + ((NG + 1) & ~1);
     static constexpr int NCOMP = S::NSTAGE == 1 ? 2 : S::NSTAGE;
-    static constexpr bool HASFIN = (MODE == COL_INV_ARGMAX);
+    static constexpr bool STATS = (MODE == COL_INV_ARGMAX_STATS);
+    static constexpr bool HASFIN = (MODE == COL_INV_ARGMAX || STATS);
     static constexpr int NPH = NCOMP + (HASFIN ? 1 : 0);
-    static constexpr int NSUM = 1;
+    static constexpr int NSUM = STATS ? 2 : 1;
     static constexpr int NBL = (S::L / S::RLAST) / S::NTS;
     static constexpr int NB0 = S::SP0 / S::NTS;
     struct Regs {
@@ -82,7 +85,7 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
     }
     static HD constexpr int sync_after(int ph)
     {
-        return (ph == NCOMP - 1 && MODE == COL_INV_ARGMAX) ? SYNC_MAXKEY : SYNC_BARRIER;
+        return (ph == NCOMP - 1 && HASFIN) ? (STATS ? SYNC_MAXKEY_SUMD : SYNC_MAXKEY) : SYNC_BARRIER;
     }
     static HD int n2of(const Params& p) { return N2C > 0 ? N2C : n2of(p); }
     static HD int nchof(const Params& p) { return NCH > 0 ? NCH : nchof(p); }
@@ -189,14 +192,17 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
             const int q = wk.y % p.nq;
             float bestv = -1.f;
             int bestc = 0;                  // output index = j + bestc; b and m are compile-time after unrolling
+            float s1 = 0.f, s2 = 0.f;
             last_stage_visit<S>(j, r.v, [&](int, float2 x, int b, int m) {
                 const float v = cnorm(x);
+                if (STATS) { s1 += sqrtf(v); s2 += v; }
                 const int c = S::NTS * b + m * S::NSLAST;
                 if (v > bestv || (NBL > 1 && v == bestv && c < bestc)) { bestv = v; bestc = c; }
             });
             const unsigned besti = (unsigned)p.nq * (unsigned)n2 + (unsigned)q +
                                    (unsigned)p.nq * (unsigned)n2of(p) * (unsigned)(j + bestc);
             r.key = make_key(bestv, besti);
+            if (STATS) { r.dsum[0] = (double)s1; r.dsum[1] = (double)s2; }
         }
     }
 
@@ -212,7 +218,7 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
         float2* sm = reinterpret_cast<float2*>(smem);
         if (tid >= NTA) {
             r.key = 0;
-            r.dsum[0] = 0.0;
+            for (int i = 0; i < NSUM; i++) r.dsum[i] = 0.0;
             return;
         }
         const int s = tid % TS, j = tid / TS;
@@ -222,7 +228,7 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
 
         if (PH == 0) {
             r.key = 0;
-            r.dsum[0] = 0.0;
+            for (int i = 0; i < NSUM; i++) r.dsum[i] = 0.0;
             if (MODE == COL_FWD) {
                 for (int t = tid; t < NG; t += NTA) {
                     const int s2 = t % TS, m = t / TS;
@@ -243,7 +249,13 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
             epilogue(p, wk, s, j, r, gtab);
         }
         if (HASFIN && PH == NCOMP) {
-            if (tid == 0) p.part_key[(i64)wk.y * p.ntx + wk.x] = r.key;
+            if (tid == 0) {
+                p.part_key[(i64)wk.y * p.ntx + wk.x] = r.key;
+                if (STATS) {
+                    p.part_stat[((i64)wk.y * p.ntx + wk.x) * 2] = r.dsum[0];
+                    p.part_stat[((i64)wk.y * p.ntx + wk.x) * 2 + 1] = r.dsum[1];
+                }
+            }
         }
     }
 };

@@ -13,15 +13,14 @@
 // MODES
 //   ROW_FWD_STORE   plain store                               (code spectrum C = fft(code))
 //   ROW_FWD_ARGMAX  |X|^2 first-max inside a window of the fftshift'ed axis (carrier estimator A3)
-//   ROW_FWD_MULCODE P = Y*conj(C) (G) or conj(Y)*C (K), sum|Y|^2, Y[0]   (A5/A6 front half)
-//   ROW_INV_TWIST   inverse over k2 of P*twist_q (polyphase q of the x3 interpolation), times the
-//                   conjugate four-step twiddle; output [lane][q][k1][n2]         (A6 back half)
+//   ROW_FWD_WINMAG  |X|^2 of every bin inside the window, stored densely (search_df candidates, A4)
+// The correlator's own row pass (forward, code product, inverse polyphases) is k_rowcorr.cuh.
 #pragma once
 #include "fft_core.cuh"
 
 namespace twstft {
 
-enum RowMode { ROW_FWD_STORE = 0, ROW_FWD_ARGMAX = 1, ROW_FWD_MULCODE = 2, ROW_INV_TWIST = 3 };
+enum RowMode { ROW_FWD_STORE = 0, ROW_FWD_ARGMAX = 1, ROW_FWD_WINMAG = 2 };
 
 struct RowParams {
     const float2* src;
@@ -36,22 +35,15 @@ struct RowParams {
     i64 win_lo, win_hi;      // inclusive window, index s of fftshift(X): s = (k + N/2) mod N
     u64* part_key;           // [lane][nblk]
     int oa1, ob1, oa2, ob2;  // k2 ranges that can intersect the window (superset; exact test follows)
-    // ROW_FWD_MULCODE
-    const float2* code;      // C in the transposed order [k1][k2]
-    int conj_mode;           // 0: Y*conj(C) (variant G)   1: conj(Y)*C (variant K)
-    double* part_energy;     // [lane][nblk]  sum |Y|^2
-    float2* y0;              // [lane] Y[0]
-    // ROW_INV_TWIST
-    const float2* twq;       // [nq][L] per-k2 twist (includes the negative-side factor), row 0 unused
-    int nq;                  // 3 (x3 interpolation) or 1
+    // ROW_FWD_WINMAG
+    float* winmag;           // [lane][win_hi - win_lo + 1]  |X|^2 at shifted index s = win_lo + i
 };
 
 template <class S, int RPC, int MODE> struct KRow {
     typedef RowParams Params;
     static const char* name()
     {
-        return MODE == ROW_FWD_STORE ? "row_fwd_store" : MODE == ROW_FWD_ARGMAX ? "row_fwd_argmax"
-             : MODE == ROW_FWD_MULCODE ? "row_fwd_mulcode" : "row_inv_twist";
+        return MODE == ROW_FWD_STORE ? "row_fwd_store" : MODE == ROW_FWD_ARGMAX ? "row_fwd_argmax" : "row_fwd_winmag";
     }
     static constexpr bool PERSISTENT = true;
     static constexpr int NTA = S::NTS * RPC;
@@ -59,11 +51,11 @@ template <class S, int RPC, int MODE> struct KRow {
     static constexpr int MINB = (S::L * RPC >= 8000) ? 2 : 4;
     typedef RowAcc<S::SP0> Acc;
     static constexpr int ROWSM = (S::R0 * Acc::BSTRIDE + 1) & ~1;      // padded row (float2 units)
-    static constexpr int NG = (MODE == ROW_INV_TWIST) ? RPC * S::RLAST : 0;
+    static constexpr int NG = 0;
     static constexpr int OFF_G = S::BLOB_PAD;
     static constexpr int OFF_DATA = OFF_G + ((NG + 1) & ~1);
     static constexpr int NCOMP = S::NSTAGE == 1 ? 2 : S::NSTAGE;       // 1-stage: phase 0 = tables only
-    static constexpr bool HASFIN = (MODE == ROW_FWD_ARGMAX || MODE == ROW_FWD_MULCODE);
+    static constexpr bool HASFIN = (MODE == ROW_FWD_ARGMAX);
     static constexpr int NPH = NCOMP + (HASFIN ? 1 : 0);
     static constexpr int NSUM = 1;
     static constexpr int NBL = (S::L / S::RLAST) / S::NTS;     // butterflies per thread in the last stage
@@ -79,12 +71,10 @@ template <class S, int RPC, int MODE> struct KRow {
     }
     static HD constexpr int sync_after(int ph)
     {
-        return (ph == NCOMP - 1) ? (MODE == ROW_FWD_ARGMAX ? SYNC_MAXKEY : (MODE == ROW_FWD_MULCODE ? SYNC_SUMD : SYNC_BARRIER))
-                                 : SYNC_BARRIER;
+        return (ph == NCOMP - 1 && MODE == ROW_FWD_ARGMAX) ? SYNC_MAXKEY : SYNC_BARRIER;
     }
-    // work decomposition: item w -> (x = w % gx, lane = w / gx); for ROW_INV_TWIST x = rowblk*nq + q
-    // (q fastest, so the CTAs that re-read the same rows of P run together and hit in L2)
-    static HD int gx(const Params& p) { return p.nblk * (MODE == ROW_INV_TWIST ? p.nq : 1); }
+    // work decomposition: item w -> (rowblk = w % nblk, lane = w / nblk)
+    static HD int gx(const Params& p) { return p.nblk; }
     static HD i64 total_work(const Params& p) { return (i64)gx(p) * p.nlanes; }
     static HD int niter(const Params& p, int bx, int gdim)
     {
@@ -99,8 +89,8 @@ template <class S, int RPC, int MODE> struct KRow {
         const int x = (int)(w % g);
         Work k;
         k.lane = w / g;
-        k.rowblk = MODE == ROW_INV_TWIST ? x / p.nq : x;
-        k.q = MODE == ROW_INV_TWIST ? x % p.nq : 0;
+        k.rowblk = x;
+        k.q = 0;
         return k;
     }
 
@@ -121,18 +111,7 @@ template <class S, int RPC, int MODE> struct KRow {
     static HD void load0(const Params& p, const Work& wk, int rl, int j, Regs& r)
     {
         const float2* xj = p.src + wk.lane * p.N + (i64)(wk.rowblk * RPC + rl) * S::L + j;
-        if (MODE == ROW_INV_TWIST) {
-            const int q = wk.q;
-            const float2* tj = p.twq + (i64)q * S::L + j;
-#pragma unroll
-            for (int b = 0; b < NB0; b++)
-#pragma unroll
-                for (int m = 0; m < S::R0; m++) {
-                    float2 z = xj[S::NTS * b + m * S::SP0];
-                    if (q > 0) z = cmul(z, tj[S::NTS * b + m * S::SP0]);
-                    r.v[b * S::R0 + m] = cswap(z);
-                }
-        } else {
+        {
 #pragma unroll
             for (int b = 0; b < NB0; b++)
 #pragma unroll
@@ -171,30 +150,22 @@ template <class S, int RPC, int MODE> struct KRow {
                 }
             });
             r.key = best;
-        } else if (MODE == ROW_FWD_MULCODE) {
-            float2* d = p.dst + lane * p.N + rowoff;
-            const float2* c = p.code + rowoff;
-            float e = 0.f;
-            const int cm = p.conj_mode;
-            last_stage_visit<S>(j, r.v, [&](int o, float2 x, int, int) {
-                float2 cc = c[o];
-                e += cnorm(x);
-                d[o] = cm ? cmul(cconj(x), cc) : cmulc(x, cc);
-            });
-            if (row == 0 && j == 0) p.y0[lane] = r.v[0];
-            r.dsum[0] = (double)e;
-        } else {  // ROW_INV_TWIST
-            const int q = wk.q;
-            float2* d = p.dst + (lane * p.nq + q) * p.N + rowoff;
-            const float2* gr = g + rl * S::RLAST;
-            float2 base[NBL];
+        } else {  // ROW_FWD_WINMAG: same window test as the arg-max, values stored instead of reduced
+            const i64 half = p.N / 2;
+            const i64 wlen = p.win_hi - p.win_lo + 1;
+            float* wm = p.winmag + lane * wlen;
+            unsigned mask[NBL];
 #pragma unroll
             for (int b = 0; b < NBL; b++) {
                 const int jb = j + S::NTS * b;
-                base[b] = cis_cycles((double)((i64)row * jb) * p.invN + (double)((i64)q * row) * p.invM);
+                mask[b] = slot_mask(p.oa1, p.ob1, jb) | slot_mask(p.oa2, p.ob2, jb);
             }
             last_stage_visit<S>(j, r.v, [&](int o, float2 x, int b, int m) {
-                d[o] = cmul(cswap(x), cmul(base[b], gr[m]));
+                if (mask[b] & (1u << m)) {
+                    i64 s = (i64)row + (i64)p.N1 * o + half;
+                    if (s >= p.N) s -= p.N;
+                    if (s >= p.win_lo && s <= p.win_hi) wm[s - p.win_lo] = cnorm(x);
+                }
             });
         }
     }
@@ -222,13 +193,6 @@ template <class S, int RPC, int MODE> struct KRow {
         if (PH == 0) {
             r.key = 0;
             r.dsum[0] = 0.0;
-            if (MODE == ROW_INV_TWIST) {
-                for (int t = tid; t < NG; t += NTA) {
-                    const int rl2 = t / S::RLAST, m = t % S::RLAST;
-                    const i64 row2 = (i64)wk.rowblk * RPC + rl2;
-                    gtab[t] = cis_cycles((double)(row2 * S::NSLAST * m) * p.invN);
-                }
-            }
         }
         if (PH == (S::NSTAGE == 1 ? 1 : 0)) {
             load0(p, wk, rl, j, r);
@@ -243,7 +207,6 @@ template <class S, int RPC, int MODE> struct KRow {
         if (HASFIN && PH == NCOMP) {
             if (tid == 0) {
                 if (MODE == ROW_FWD_ARGMAX) p.part_key[wk.lane * p.nblk + wk.rowblk] = r.key;
-                if (MODE == ROW_FWD_MULCODE) p.part_energy[wk.lane * p.nblk + wk.rowblk] = r.dsum[0];
             }
         }
     }

@@ -186,7 +186,7 @@ struct PeakEvalParams {
 // One CTA per (lag, lane): prnmap[p] = sum_k1 B[q][k1][n2] exp(+2 pi i k1 n1 / L1) with
 // p = nq*(n1*N2 + n2) + q, i.e. one output of the inverse column transform evaluated directly
 // (fp64 twiddles and accumulation) -- a few thousand terms instead of a pass over the spectrum.
-struct KPeakEval {
+template <int NPTS, int DLO> struct KPeakEvalT {
     typedef PeakEvalParams Params;
     static const char* name() { return "peak_eval"; }
     static constexpr bool PERSISTENT = false;
@@ -209,7 +209,7 @@ struct KPeakEval {
         } else if (PH == 1) {
             const i64 M = (i64)p.nq * p.N;
             const i64 p0 = (i64)key_index(r.key);
-            i64 pp = (p0 + PEAK_DLO + d) % M;
+            i64 pp = (p0 + DLO + d) % M;
             if (pp < 0) pp += M;
             const int q = (int)(pp % p.nq);
             const i64 m = pp / p.nq;
@@ -225,12 +225,14 @@ struct KPeakEval {
             r.dsum[0] = sr;
             r.dsum[1] = si;
         } else if (tid == 0) {
-            p.part[(lane * PEAK_NPTS + d) * 2] = r.dsum[0];
-            p.part[(lane * PEAK_NPTS + d) * 2 + 1] = r.dsum[1];
+            p.part[(lane * NPTS + d) * 2] = r.dsum[0];
+            p.part[(lane * NPTS + d) * 2 + 1] = r.dsum[1];
             if (d == 0) p.p0_out[lane] = (i64)key_index(r.key);
         }
     }
 };
+
+typedef KPeakEvalT<PEAK_NPTS, PEAK_DLO> KPeakEval;
 
 // One result row per lane = one row of the reference's .mat variables.
 struct Result {
@@ -258,6 +260,7 @@ struct PeakFinParams {
     int nq;
     int variant;               // 0 = G (godual_ranging.m), 1 = K (claudio_aligned_code_*_separate.m)
     int ddof;                  // 1 = Octave var, 0 = numpy var
+    double code_pow;           // mean |code|^2 (sum|yincode|^2 = code_pow * sum|yint|^2)
     Result* out;               // [lane]
 };
 struct KPeakFinal {
@@ -329,7 +332,7 @@ struct KPeakFinal {
         }
         const double E = r.dsum[2 * PEAK_NPTS];
         const double n = (double)p.N, m = (double)M;
-        const double var_c = (E / m - m * (mr * mr + mi * mi)) / (m - (double)p.ddof);
+        const double var_c = (p.code_pow * E / m - m * (mr * mr + mi * mi)) / (m - (double)p.ddof);
         const float2 y0 = p.y0[lane];
         const double y0n = (double)y0.x * (double)y0.x + (double)y0.y * (double)y0.y;
         o.SNRr = mr * mr / var_c;
@@ -340,6 +343,67 @@ struct KPeakFinal {
         o.puissancenoise = var_c;
         o.carrier_bin = (double)p.sbin[lane];
         o.status = status;
+        p.out[lane] = o;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// KBankFinal: per-bin metric of search_df / the Doppler bank (claudio_aligned_code_re_separate.m:33-42):
+//   prnmap=abs(ifft(fcode.*conj(fft(y)))); [prnsig,b]=max(prnmap); prnmap(b-5:b+5)=0; snr=prnsig^2/var(prnmap)
+// from the tile sums of |z|, |z|^2 (inverse column pass) and the 11 lags around the maximum (KPeakEvalT).
+constexpr int BANK_NPTS = 11;
+constexpr int BANK_DLO = -5;
+struct BankRow { double b0, prnsig, metric, status; };
+struct BankFinParams {
+    const double* part_stat;   // [lane][npart][2]
+    int npart;
+    const double* lags;        // [lane][BANK_NPTS][2]  unnormalised correlation around the maximum
+    const i64* p0;             // [lane]
+    i64 N;
+    BankRow* out;              // [lane]
+};
+struct KBankFinal {
+    typedef BankFinParams Params;
+    static const char* name() { return "bank_final"; }
+    static constexpr bool PERSISTENT = false;
+    static constexpr int NT = 256, MINB = 4, NPH = 2, NSUM = 2;
+    struct Regs { u64 key; double dsum[NSUM]; };
+    static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }
+    static HD constexpr int sync_after(int) { return SYNC_SUMD; }
+    template <int PH> static HD void phase(const Params& p, const Blk& blk, int tid, Regs& r, unsigned char*)
+    {
+        const i64 lane = blk.y;
+        if (PH == 0) {
+            double s1 = 0.0, s2 = 0.0;
+            for (int i = tid; i < p.npart; i += NT) {
+                s1 += p.part_stat[(lane * p.npart + i) * 2];
+                s2 += p.part_stat[(lane * p.npart + i) * 2 + 1];
+            }
+            r.dsum[0] = s1;
+            r.dsum[1] = s2;
+            return;
+        }
+        if (tid != 0) return;
+        const double n = (double)p.N;
+        double s1 = r.dsum[0], s2 = r.dsum[1], peak = 0.0;
+        for (int d = 0; d < BANK_NPTS; d++) {           // the zeroed samples b-5..b+5 leave both sums
+            const double re = p.lags[(lane * BANK_NPTS + d) * 2], im = p.lags[(lane * BANK_NPTS + d) * 2 + 1];
+            const double a2 = re * re + im * im;
+            s1 -= sqrt(a2);
+            s2 -= a2;
+            if (d == -BANK_DLO) peak = sqrt(a2);
+        }
+        s1 /= n;                                        // ifft scale 1/N on the magnitudes
+        s2 /= n * n;
+        peak /= n;
+        const double mu = s1 / n;
+        const double var = (s2 - n * mu * mu) / (n - 1.0);
+        BankRow o;
+        const i64 b0 = p.p0[lane];
+        o.b0 = (double)b0;
+        o.prnsig = peak;
+        o.metric = peak * peak / var;
+        o.status = (b0 < 5 || b0 > p.N - 6) ? 1.0 : 0.0;   // Octave's b-5:b+5 would leave the array
         p.out[lane] = o;
     }
 };

@@ -49,9 +49,11 @@ public:
     virtual int row_len() const = 0;
     virtual size_t bytes_per_lane() const = 0;
     virtual int setup(Backend* be, int max_lanes, int nq) = 0;
-    virtual int build_code(const unsigned char* d_bits, int rep, int qpsk, float2 mean) = 0;
+    virtual int build_code(const unsigned char* d_bits, int rep, int qpsk, float2 mean, double code_pow) = 0;
     virtual int estimate(const RunArgs& a, const EstimatorCfg& e) = 0;   // -> d_df/d_sbin (+ derotation tables)
     virtual int correlate(const RunArgs& a) = 0;
+    virtual int window_spectrum(const RunArgs& a, const EstimatorCfg& e, float* d_win) = 0;
+    virtual int bank(const RunArgs& a, int sub_mean, BankRow* d_out) = 0;
     virtual int debug_fetch(int what, int lane, void* host_out, size_t bytes) = 0;
 };
 
@@ -69,7 +71,7 @@ public:
     bool have_means = false;   // estimate() already left the window means in d_sums
     float2 *d_blob_c = nullptr, *d_blob_r = nullptr, *d_code = nullptr, *d_qconst = nullptr;
     float2 *d_A = nullptr, *d_B = nullptr;
-    double *d_sums = nullptr, *d_energy = nullptr, *d_df = nullptr, *d_peakpart = nullptr;
+    double *d_sums = nullptr, *d_energy = nullptr, *d_df = nullptr, *d_peakpart = nullptr, *d_stat = nullptr, *d_bankpart = nullptr;
     u64 *d_keyrow = nullptr, *d_keycol = nullptr;
     i64 *d_sbin = nullptr, *d_p0 = nullptr;
     float2 *d_y0 = nullptr, *d_lrow = nullptr, *d_lcol = nullptr;
@@ -81,7 +83,7 @@ public:
     {
         if (!be) return;
         void* all[] = {d_blob_c, d_blob_r, d_code, d_qconst, d_A, d_B, d_sums, d_energy, d_df, d_peakpart,
-                       d_keyrow, d_keycol, d_sbin, d_p0, d_y0, d_lrow, d_lcol};
+                       d_keyrow, d_keycol, d_sbin, d_p0, d_y0, d_lrow, d_lcol, d_stat, d_bankpart};
         for (void* p : all) be->free(p);
     }
     i64 size() const override { return N; }
@@ -137,6 +139,8 @@ public:
         d_energy = dalloc<double>((size_t)lanes * NROWBLK);
         d_df = dalloc<double>(lanes);
         d_peakpart = dalloc<double>((size_t)lanes * 2 * PEAK_NPTS);
+        d_stat = dalloc<double>((size_t)lanes * NCOLTILE_I * 2);
+        d_bankpart = dalloc<double>((size_t)lanes * 2 * BANK_NPTS);
         d_keyrow = dalloc<u64>((size_t)lanes * NROWBLK);
         d_keycol = dalloc<u64>((size_t)lanes * nq * NCOLTILE_I);
         d_sbin = dalloc<i64>(lanes);
@@ -147,15 +151,17 @@ public:
         return be->ok() ? 0 : -1;
     }
 
-    int build_code(const unsigned char* d_bits, int rep, int qpsk, float2 mean) override
+    double code_pow = 1.0;     // mean |code|^2: 1 for the +/-1 BPSK replica, ~0.5 for the QPSK one
+    int build_code(const unsigned char* d_bits, int rep, int qpsk, float2 mean, double cpow) override
     {
+        code_pow = cpow;
         ColParams c{};
         c.src = d_bits; c.dst = d_A; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.invN = 1.0 / (double)N; c.nch = 1;
         c.rep = rep; c.qpsk = qpsk; c.code_mean = mean; c.nq = 1; c.ntx = NCOLTILE; c.ny = 1;
         typedef KCol<CS, TS, SRC_BITS, COL_FWD, 0, N2, 1> KC;
         be->template launch<KC>(pgrid<KC>(NCOLTILE), c);
         RowParams r{};
-        r.src = d_A; r.dst = d_code; r.blob = d_blob_r; r.N = N; r.N1 = L1; r.invN = 1.0 / (double)N; r.invM = 1.0 / ((double)nq * (double)N); r.nq = 1; r.nblk = NROWBLK;
+        r.src = d_A; r.dst = d_code; r.blob = d_blob_r; r.N = N; r.N1 = L1; r.invN = 1.0 / (double)N; r.invM = 1.0 / ((double)nq * (double)N); r.nblk = NROWBLK;
         r.nlanes = 1;
         typedef KRow<RS, RPC, ROW_FWD_STORE> KR;
         be->template launch<KR>(pgrid<KR>(NROWBLK), r);
@@ -203,17 +209,17 @@ public:
         be->template launch<KDfFinal>(dim3(d.nsplit, lanes, 1), d);
     }
 
-    int estimate(const RunArgs& a, const EstimatorCfg& e) override
+    // forward transform of x^p and the row-pass parameters of the estimator window
+    RowParams estimator_front(const RunArgs& a, const EstimatorCfg& e)
     {
         const int lanes = a.nrec * a.nch;
-        if (lanes > max_lanes) return -2;
         if (e.sub_mean) means(a);
         have_means = e.sub_mean != 0;
         if (e.power == 4) col_raw<4>(a, e.sub_mean);
         else col_raw<2>(a, e.sub_mean);
         RowParams r{};
         r.src = d_A; r.blob = d_blob_r; r.N = N; r.N1 = L1; r.invN = 1.0 / (double)N; r.invM = 1.0 / ((double)nq * (double)N); r.win_lo = e.win_lo; r.win_hi = e.win_hi;
-        r.part_key = d_keyrow; r.nq = 1; r.nblk = NROWBLK;
+        r.part_key = d_keyrow; r.nblk = NROWBLK;
         {   // k2 ranges whose bins k = k1 + L1*k2 can intersect the window (bins as signed frequencies)
             const i64 ka = e.win_lo - N / 2, kb = e.win_hi - N / 2;     // signed bin range [ka, kb]
             auto lo_of = [&](i64 k) { i64 v = (k - (L1 - 1)) / L1; if ((k - (L1 - 1)) < 0 && (k - (L1 - 1)) % L1) v--; return v; };
@@ -225,9 +231,63 @@ public:
             if (r.oa2 < 0) r.oa2 = 0;
         }
         r.nlanes = lanes;
+        return r;
+    }
+
+    int estimate(const RunArgs& a, const EstimatorCfg& e) override
+    {
+        const int lanes = a.nrec * a.nch;
+        if (lanes > max_lanes) return -2;
+        RowParams r = estimator_front(a, e);
         typedef KRow<RS, RPC, ROW_FWD_ARGMAX> KR;
         be->template launch<KR>(pgrid<KR>((i64)NROWBLK * lanes), r);
         df_final(a, &e);
+        return be->ok() ? 0 : -1;
+    }
+
+    // |fft(x^p)|^2 of every bin of the estimator window -> d_win[lane][win_hi-win_lo+1]  (search_df, A4)
+    int window_spectrum(const RunArgs& a, const EstimatorCfg& e, float* d_win) override
+    {
+        const int lanes = a.nrec * a.nch;
+        if (lanes > max_lanes) return -2;
+        RowParams r = estimator_front(a, e);
+        have_means = false;
+        r.winmag = d_win;
+        typedef KRow<RS, RPC, ROW_FWD_WINMAG> KR;
+        be->template launch<KR>(pgrid<KR>((i64)NROWBLK * lanes), r);
+        return be->ok() ? 0 : -1;
+    }
+
+    // 1x correlation of every lane against the code, conj(Y)*C as in search_df, and the per-lane metric
+    // max^2/var with b-5..b+5 zeroed (claudio_aligned_code_re_separate.m:33-42) -> d_out[lane]
+    int bank(const RunArgs& a, int sub_mean, BankRow* d_out) override
+    {
+        const int lanes = a.nrec * a.nch;
+        if (lanes > max_lanes) return -2;
+        if (sub_mean) means(a);
+        have_means = false;
+        df_final(a, nullptr);
+        col_raw<1>(a, sub_mean);
+        RowCorrParams r{};
+        r.src = d_A; r.dst = d_B; r.blob = d_blob_r; r.code = d_code; r.qconst = d_qconst; r.N = N; r.N1 = L1;
+        r.invN = 1.0 / (double)N; r.invM = 1.0 / (double)N; r.nlanes = lanes; r.nblk = NROWBLK;
+        r.conj_mode = 1; r.part_energy = d_energy; r.y0 = d_y0;
+        typedef KRowCorr<RS, RPC, 1> K1;
+        i64 g = (i64)NROWBLK * lanes;
+        if (g > (i64)be->num_sms * K1::MINB) g = (i64)be->num_sms * K1::MINB;
+        be->template launch<K1>(dim3((unsigned)g, 1, 1), r);
+        ColParams c{};
+        c.src = d_B; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.invN = 1.0 / (double)N; c.nch = 1; c.nq = 1;
+        c.part_key = d_keycol; c.part_stat = d_stat; c.ntx = NCOLTILE_I; c.ny = lanes;
+        typedef KCol<CS, TSI, SRC_CF32, COL_INV_ARGMAX_STATS, 0, N2, 1> KCS;
+        be->template launch<KCS>(pgrid<KCS>((i64)c.ntx * c.ny), c);
+        PeakEvalParams pe{};
+        pe.part_key = d_keycol; pe.npart = NCOLTILE_I; pe.B = d_B; pe.N = N; pe.nq = 1; pe.L1 = L1; pe.N2 = N2;
+        pe.p0_out = d_p0; pe.part = d_bankpart;
+        be->template launch<KPeakEvalT<BANK_NPTS, BANK_DLO>>(dim3(BANK_NPTS, lanes, 1), pe);
+        BankFinParams bf{};
+        bf.part_stat = d_stat; bf.npart = NCOLTILE_I; bf.lags = d_bankpart; bf.p0 = d_p0; bf.N = N; bf.out = d_out;
+        be->template launch<KBankFinal>(dim3(1, lanes, 1), bf);
         return be->ok() ? 0 : -1;
     }
 
@@ -264,7 +324,7 @@ public:
         be->template launch<KPeakEval>(dim3(PEAK_NPTS, lanes, 1), pe);
         PeakFinParams pf{};
         pf.part = d_peakpart; pf.nblk = 1; pf.part_energy = d_energy; pf.nen = NROWBLK; pf.y0 = d_y0;
-        pf.p0 = d_p0; pf.df = d_df; pf.sbin = d_sbin; pf.N = N; pf.nq = nq; pf.variant = a.variant; pf.ddof = a.ddof;
+        pf.code_pow = code_pow; pf.p0 = d_p0; pf.df = d_df; pf.sbin = d_sbin; pf.N = N; pf.nq = nq; pf.variant = a.variant; pf.ddof = a.ddof;
         pf.out = a.d_out;
         be->template launch<KPeakFinal>(dim3(1, lanes, 1), pf);
         return be->ok() ? 0 : -1;

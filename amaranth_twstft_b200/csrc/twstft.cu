@@ -4,11 +4,13 @@
 #include "pipeline.cuh"
 #include <string>
 #include <vector>
+#include <algorithm>
 #include <stdio.h>
 
 using namespace twstft;
 
 static_assert(sizeof(twstft_result) == sizeof(Result), "public result row must match the device row");
+static_assert(sizeof(twstft_bank_result) == sizeof(BankRow), "public bank row must match the device row");
 
 struct twstft_plan {
     twstft_config cfg;
@@ -162,12 +164,16 @@ static int install_code(twstft_plan* p, const unsigned char* host_bits, size_t n
     if ((i64)nchips * p->cfg.samples_per_chip != p->cfg.nsamples)
         return fail(p, TWSTFT_E_ARG, "code length * samples_per_chip != nsamples");
     float2 mean = make_float2(0.f, 0.f);
+    double code_pow = 1.0;
     if (qpsk) {   // goqpsk.m:11-12 codec=codei+j*codeq; codec=codec-mean(codec)
         double sa = 0, sb = 0;
         for (size_t i = 0; i < nchips; i++) { sa += host_bits[2 * i]; sb += host_bits[2 * i + 1]; }
-        mean = make_float2((float)(sa / (double)nchips), (float)(sb / (double)nchips));
+        const double ma = sa / (double)nchips, mb = sb / (double)nchips;
+        mean = make_float2((float)ma, (float)mb);
+        // mean |codec|^2 with bits in {0,1}: E[(a-ma)^2] + E[(b-mb)^2] = ma(1-ma) + mb(1-mb)
+        code_pow = ma * (1.0 - ma) + mb * (1.0 - mb);
     }
-    if (p->pipe->build_code(p->d_bits, p->cfg.samples_per_chip, qpsk, mean) != 0)
+    if (p->pipe->build_code(p->d_bits, p->cfg.samples_per_chip, qpsk, mean, code_pow) != 0)
         return fail(p, TWSTFT_E_CUDA, p->be.err_string());
     p->be.sync();
     if (!p->be.ok()) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
@@ -396,6 +402,114 @@ int twstft_estimate_carrier(twstft_plan* p, const int16_t* iq, int on_device, si
         }
         p->be.sync();
         if (!p->be.ok()) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
+    }
+    return TWSTFT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Doppler bank (A12) and search_df (A4)
+
+// stage one window (all channels) on the device unless it is already there
+static const short2* stage_window(twstft_plan* p, const int16_t* iq, int on_device, int64_t offset)
+{
+    const short2* src = reinterpret_cast<const short2*>(iq) + (size_t)offset * p->nch;
+    if (on_device) return src;
+    if (ensure_raw(p) != 0) return nullptr;
+    p->be.h2d(p->d_raw, src, sizeof(short2) * p->raw_elems_per_rec);
+    return p->d_raw;
+}
+
+static int run_bank(twstft_plan* p, const short2* d_win, const double* dfs, size_t nbins, int sub_mean,
+                    twstft_bank_result* results)
+{
+    const int B = p->cfg.max_batch;
+    std::vector<i64> off(B, 0);
+    std::vector<double> dfl((size_t)B * p->nch);
+    p->be.h2d(p->d_off, off.data(), sizeof(i64) * B);
+    BankRow* d_rows = (BankRow*)p->d_res;                // the result staging is large enough: Result > BankRow
+    for (size_t b0 = 0; b0 < nbins; b0 += B) {
+        const int nb = (int)((nbins - b0) < (size_t)B ? (nbins - b0) : B);
+        for (int i = 0; i < nb; i++)
+            for (int c = 0; c < p->nch; c++) dfl[(size_t)i * p->nch + c] = dfs[b0 + i];
+        p->be.h2d(p->d_dfin, dfl.data(), sizeof(double) * nb * p->nch);
+        RunArgs a{};
+        a.d_raw = d_win; a.nrec = nb; a.nch = p->nch; a.rec_stride = 0; a.d_rec_offset = p->d_off;
+        a.estimate = 0; a.d_df_in = p->d_dfin; a.variant = 1; a.ddof = 1; a.fs = p->cfg.fs;
+        if (p->pipe->bank(a, sub_mean, d_rows) != 0) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
+        p->be.d2h(results + b0 * p->nch, d_rows, sizeof(BankRow) * nb * p->nch);
+        p->be.sync();
+        if (!p->be.ok()) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
+    }
+    return TWSTFT_OK;
+}
+
+int twstft_doppler_bank(twstft_plan* p, const int16_t* iq, int iq_on_device, size_t total_instants, int64_t offset,
+                        const double* dfs, size_t nbins, int sub_mean, twstft_bank_result* results)
+{
+    if (!p || !p->pipe || !iq || !dfs || !results) return TWSTFT_E_ARG;
+    if (!p->have_code) return fail(p, TWSTFT_E_NOCODE, "no PRN code installed");
+    if (offset < 0 || (size_t)(offset + p->cfg.nsamples) > total_instants)
+        return fail(p, TWSTFT_E_ARG, "window outside the buffer");
+    p->be.use();
+    const short2* d_win = stage_window(p, iq, iq_on_device, offset);
+    if (!d_win) return fail(p, TWSTFT_E_NOMEM, "device allocation failed");
+    return run_bank(p, d_win, dfs, nbins, sub_mean, results);
+}
+
+int twstft_search_df(twstft_plan* p, const int16_t* iq, int iq_on_device, size_t total_instants, int64_t offset,
+                     double df_threshold, int64_t* kbon, double* df_found, int32_t* ncand)
+{
+    if (!p || !p->pipe || !iq || !kbon) return TWSTFT_E_ARG;
+    if (!p->have_code) return fail(p, TWSTFT_E_NOCODE, "no PRN code installed");
+    if (offset < 0 || (size_t)(offset + p->cfg.nsamples) > total_instants)
+        return fail(p, TWSTFT_E_ARG, "window outside the buffer");
+    p->be.use();
+    const short2* d_win = stage_window(p, iq, iq_on_device, offset);
+    if (!d_win) return fail(p, TWSTFT_E_NOMEM, "device allocation failed");
+    const EstimatorCfg& e = p->est;
+    const size_t wlen = (size_t)(e.win_hi - e.win_lo + 1);
+    float* d_mag = (float*)p->be.alloc(sizeof(float) * wlen * p->nch);
+    if (!p->be.ok()) return fail(p, TWSTFT_E_NOMEM, "device allocation failed");
+    i64 zero = 0;
+    p->be.h2d(p->d_off, &zero, sizeof(i64));
+    RunArgs a{};
+    a.d_raw = d_win; a.nrec = 1; a.nch = p->nch; a.rec_stride = 0; a.d_rec_offset = p->d_off;
+    a.estimate = 1; a.variant = p->cfg.variant; a.ddof = p->cfg.ddof; a.fs = p->cfg.fs;
+    int rc = TWSTFT_OK;
+    std::vector<float> mag(wlen * p->nch);
+    if (p->pipe->window_spectrum(a, e, d_mag) != 0) rc = fail(p, TWSTFT_E_CUDA, p->be.err_string());
+    if (rc == TWSTFT_OK) {
+        p->be.d2h(mag.data(), d_mag, sizeof(float) * wlen * p->nch);
+        p->be.sync();
+        if (!p->be.ok()) rc = fail(p, TWSTFT_E_CUDA, p->be.err_string());
+    }
+    p->be.free(d_mag);
+    if (rc != TWSTFT_OK) return rc;
+    for (int c = 0; c < p->nch; c++) {
+        // ktmp=find(d2(k) > median(d2(k))*df_threshold)   re_separate.m:29
+        std::vector<double> v(wlen);
+        for (size_t i = 0; i < wlen; i++) v[i] = sqrt((double)mag[(size_t)c * wlen + i]);
+        std::vector<double> s(v);
+        std::nth_element(s.begin(), s.begin() + wlen / 2, s.end());
+        double med = s[wlen / 2];
+        if (wlen % 2 == 0) med = 0.5 * (med + *std::max_element(s.begin(), s.begin() + wlen / 2));
+        std::vector<i64> cand;
+        for (size_t i = 0; i < wlen; i++)
+            if (v[i] > med * df_threshold) cand.push_back(e.win_lo + (i64)i);
+        kbon[c] = 0;
+        if (df_found) df_found[c] = 0.0;
+        if (ncand) ncand[c] = (int32_t)cand.size();
+        if (cand.empty() || cand.size() >= 100) continue;          // re_separate.m:31
+        std::vector<double> dfs(cand.size());
+        for (size_t i = 0; i < cand.size(); i++) dfs[i] = axis_value(e, cand[i]) / (double)e.power;
+        std::vector<twstft_bank_result> rows(cand.size() * p->nch);
+        rc = run_bank(p, d_win, dfs.data(), dfs.size(), e.sub_mean, rows.data());
+        if (rc != TWSTFT_OK) return rc;
+        for (size_t i = 0; i < cand.size(); i++)
+            if (rows[i * p->nch + c].metric > 100.0) {             // "SNR > 20 dB", last accepted wins (:42)
+                kbon[c] = cand[i] + 1;
+                if (df_found) df_found[c] = dfs[i];
+            }
     }
     return TWSTFT_OK;
 }

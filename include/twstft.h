@@ -15,6 +15,9 @@
  *   twstft_process_windows  processing(d,k,df) / processing(d,df) of variant K   claudio_aligned_code_lo_separate.m:24-77
  *                                                                                 claudio_aligned_code_re_separate.m:48-101
  *   twstft_estimate_carrier  d2=fftshift(abs(fft(d.^2))); [~,df]=max(d2(k))      godual_ranging.m:14-15, lo_separate.m:126-129
+ *   twstft_doppler_bank  per-bin body of search_df over a grid of offsets (cross-ambiguity)
+ *                                                                                 claudio_aligned_code_re_separate.m:33-42
+ *   twstft_search_df     k=search_df(d,k,df_threshold)                            claudio_aligned_code_re_separate.m:26-46
  *   twstft_result        one row of the .mat variables                            godual_ranging.m:128-130, lo_separate.m:166
  *
  * Conventions: plain C, caller owns every host buffer, the plan owns device memory and streams,
@@ -115,6 +118,27 @@ int twstft_process_windows(twstft_plan* plan, const int16_t* iq, int iq_on_devic
 /* Carrier estimator alone (A3): df[record*nch+ch], bins[...] = 0-based index on the shifted axis. */
 int twstft_estimate_carrier(twstft_plan* plan, const int16_t* iq, int iq_on_device, size_t nrecords,
                             double* df, int64_t* bins);
+
+/* One Doppler bin: [prnsig,b]=max(abs(ifft(fcode.*conj(fft(y))))) at 1x, metric = prnsig^2/var with b-5..b+5 zeroed. */
+typedef struct twstft_bank_result {
+    double b0;      /* 0-based index of the maximum (Octave b = b0+1) */
+    double prnsig;  /* magnitude of the maximum (ifft scale 1/N) */
+    double metric;  /* prnsig^2 / var(prnmap), the "snr" of search_df */
+    double status;  /* bit0: b within 5 samples of the array edge (Octave's b-5:b+5 would fail; the zeroing wraps) */
+} twstft_bank_result;
+
+/* Cross-ambiguity search: the window of N sample instants starting at `offset` of a (host or device) buffer
+ * is derotated by every dfs[i] and correlated against the code; results[i*nch + ch].
+ * sub_mean != 0 removes the window mean first (the caller of processing() does, search_df does not). */
+int twstft_doppler_bank(twstft_plan* plan, const int16_t* iq, int iq_on_device, size_t total_instants, int64_t offset,
+                        const double* dfs, size_t nbins, int sub_mean, twstft_bank_result* results);
+
+/* search_df on one window: candidates = bins of the plan's estimator window whose |fft(x^p)| exceeds
+ * df_threshold*median; if there are 1..99 each is tested with the bank body and the LAST one whose metric
+ * exceeds 100 wins.  kbon[ch] = its 1-based index on the fftshift'ed axis (0 = none), df_found[ch] = freq/p,
+ * ncand[ch] = number of candidates.  (The reference runs it on 2-s blocks; here the block is the plan window.) */
+int twstft_search_df(twstft_plan* plan, const int16_t* iq, int iq_on_device, size_t total_instants, int64_t offset,
+                     double df_threshold, int64_t* kbon, double* df_found, int32_t* ncand);
 
 /* Pinned host memory for the end-to-end path, device memory helpers for device-resident inputs. */
 void* twstft_host_alloc(size_t bytes);

@@ -128,7 +128,9 @@ def processing_G(d, k, freq, fcode, code, fs=FS, power=2, fine_freq=False, ddof=
     yint = _fft.ifft(_pad3(ffty))
     codetmp = np.repeat(code, 3)
     # yincode=[yint(indice-1:end);yint(1:indice-2)].*codetmp  -> rotate left by indice-2 = p0-1
-    yincode = np.roll(yint, -(p0 - 1)) * codetmp
+    # Complex (QPSK) replica: despread with conj(code).  The reference only ever does this with a real
+    # code (goqpsk.m:39-45 stops at the peak), for which conj() changes nothing.
+    yincode = np.roll(yint, -(p0 - 1)) * np.conj(codetmp)
     v = _var(yincode, ddof)
     mr, mi = np.mean(yincode.real), np.mean(yincode.imag)
     out.update(indice=p0 + 1, p0=p0, correction=float(correction), xval=complex(xval),

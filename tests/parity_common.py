@@ -73,3 +73,73 @@ def run_variant_g(lib, n, seeds, fs=5e6, window=(-20000.0, 20000.0), max_batch=2
         for ch in (1, 2):
             assert_row_matches(res[i, ch - 1], ref[ch], where=f"N={n} seed={seeds[i]} ch{ch}")
     return res
+
+
+def run_qpsk(lib, n=200000, seeds=(41, 42), window=(-40000.0, 40000.0)):
+    """configs[2]: QPSK record, x^4 carrier estimator (df=freq/4, Doc/07_Demodulation.md:60-63), replica
+    (codei+j*codeq)-mean of experiments/220822_qpsk_vs_bpsk/goqpsk.m:10-16, 100 kchip code (17 bits, taps 9/15)."""
+    fs = 5e6
+    chips = prn.prn_file_bytes(17, n // 2, 9, 15)
+    code = oc.code_qpsk(chips)
+    recs = [synth.record_pair(code, s, fs=fs, ch1=dict(snr_db=0.0), ch2=dict(snr_db=3.0))[0] for s in seeds]
+    with Correlator(nsamples=n, fs=fs, modulation="qpsk", window_hz=window, max_batch=2, lib=lib) as cor:
+        cor.set_code(chips, qpsk=True)
+        res = cor.process(np.stack(recs))
+    freq = oc.freq_axis_G(fs, n)
+    k = oc.window(freq, window[0], window[1])
+    fcode = oc.fcode_G(code)
+    for i, raw in enumerate(recs):
+        ref = oc.record_G(raw, k, freq, fcode, code, fs=fs, power=4)
+        for ch in (1, 2):
+            assert_row_matches(res[i, ch - 1], ref[ch], where=f"QPSK seed={seeds[i]} ch{ch}")
+
+
+def run_variant_k(lib, n, delay, df=1234.5, seed=77):
+    """processing(d,k,df) of claudio_aligned_code_lo_separate.m:24-77 on one single-channel window."""
+    bits, code = make_code(n)
+    raw, _ = synth.record_single(code, seed, delay=delay, df=df, snr_db=-5.0)
+    with Correlator(nsamples=n, variant="K", layout="single", max_batch=2, lib=lib) as cor:
+        cor.set_code(bits)
+        res = cor.process_windows(raw, [0], [df])
+    d = oc.unpack_single(raw)
+    ref = oc.processing_K(d - d.mean(), df, oc.fcode_K(code), code)
+    assert_row_matches(res[0, 0], ref, where=f"K N={n} delay={delay}")
+
+
+def run_doppler_bank(lib, n=10000, nbins=16, span=2000.0, true_df=437.0, seed=3, snr_db=-10.0, check_every=1):
+    """configs[3]: one record correlated over a bank of Doppler bins (the per-bin body of search_df,
+    claudio_aligned_code_re_separate.m:33-42): peak index bit-exact, magnitude and metric to 1e-4."""
+    bits, code = make_code(n)
+    raw, _ = synth.record_single(code, seed, delay=0.37 * n + 0.4, df=true_df, snr_db=snr_db)
+    dfs = np.linspace(-span, span, nbins)
+    with Correlator(nsamples=n, variant="K", layout="single", max_batch=5, lib=lib) as cor:
+        cor.set_code(bits)
+        res = cor.doppler_bank(raw, dfs, sub_mean=True)
+    d = oc.unpack_single(raw)
+    chk = list(range(0, nbins, check_every))        # the oracle costs ~2 s per bin at N = 5e6
+    b0s, sigs, mets = oc.doppler_bank(d - d.mean(), dfs[chk], oc.fcode_K(code))
+    b0, sig, met = dict(zip(chk, b0s)), dict(zip(chk, sigs)), dict(zip(chk, mets))
+    for i in chk:
+        assert int(res[i, 0]["b0"]) == b0[i], f"bin {i}: peak {res[i, 0]['b0']} vs {b0[i]}"
+        assert abs(res[i, 0]["prnsig"] / sig[i] - 1) < 1e-4, f"bin {i}: prnsig"
+        assert abs(res[i, 0]["metric"] / met[i] - 1) < 1e-3, f"bin {i}: metric {res[i, 0]['metric']} vs {met[i]}"
+    return res, dfs
+
+
+def run_search_df(lib, n=250000, true_df=51234.0, seed=8):
+    """k=search_df(d,k,df_threshold) of claudio_aligned_code_re_separate.m:26-46 on one window; remote window."""
+    fs = 5e6
+    bits, code = make_code(n)
+    raw, _ = synth.record_single(code, seed, delay=1234.25, df=true_df, snr_db=0.0, fs=fs)
+    win = (92000.0, 108000.0)
+    with Correlator(nsamples=n, fs=fs, variant="K", layout="single", freq_axis="G", window_hz=win, est_sub_mean=0,
+                    max_batch=4, lib=lib) as cor:
+        cor.set_code(bits)
+        kbon, df, ncand = cor.search_df(raw, 20.0)
+    d = oc.unpack_single(raw)
+    freq = oc.freq_axis_G(fs, n)
+    k = oc.window(freq, *win)
+    kref, tried = oc.search_df(d, k, 20.0, freq, oc.fcode_K(code), fs=fs)
+    assert ncand[0] == len(tried), (ncand, tried)
+    assert kbon[0] == kref, (kbon, kref, tried)
+    assert kref > 0 and df[0] == freq[kref - 1] / 2

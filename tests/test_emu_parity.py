@@ -85,24 +85,10 @@ def test_batching_is_transparent():
         assert np.array_equal(a[nm], b[nm]), nm
 
 
-def _k_case(n, seed, delay, df, snr_db=-5.0):
-    bits, code = pc.make_code(n)
-    raw, tr = synth.record_single(code, seed, delay=delay, df=df, snr_db=snr_db)
-    return bits, code, raw
-
-
 @pytest.mark.parametrize("delay", [0.0, 0.2, 1.0 / 3.0, 17.4, 4321.7, 9999.6])
 def test_variant_k_windows(delay):
     """processing(d,k,df) of claudio_aligned_code_lo_separate.m:24-77 incl. the neighbour-wrap quirks."""
-    n = 10000
-    bits, code, raw = _k_case(n, 77, delay, 1234.5)
-    df = 1234.5
-    with Correlator(nsamples=n, variant="K", layout="single", max_batch=2, lib=pc.EMU_LIB) as cor:
-        cor.set_code(bits)
-        res = cor.process_windows(raw, [0], [df])
-    d = oc.unpack_single(raw)
-    ref = oc.processing_K(d - d.mean(), df, oc.fcode_K(code), code)
-    pc.assert_row_matches(res[0, 0], ref, where=f"K delay={delay}")
+    pc.run_variant_k(pc.EMU_LIB, 10000, delay)
 
 
 def test_variant_k_window_offsets_in_long_buffer():
@@ -152,3 +138,16 @@ def test_estimate_carrier_only():
         for ch, d in enumerate((d1, d2)):
             s, f = oc.carrier_estimate(d - d.mean(), k, freq)
             assert bins[i, ch] == s and df[i, ch] == f
+
+
+def test_qpsk_x4_estimator_and_complex_replica():
+    pc.run_qpsk(pc.EMU_LIB)
+
+
+def test_doppler_bank_matches_search_df_body():
+    res, dfs = pc.run_doppler_bank(pc.EMU_LIB)
+    assert abs(dfs[int(np.argmax(res["metric"][:, 0]))] - 437.0) <= (dfs[1] - dfs[0])
+
+
+def test_search_df_finds_the_carrier():
+    pc.run_search_df(pc.EMU_LIB)

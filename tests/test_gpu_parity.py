@@ -42,3 +42,52 @@ def test_variant_g_small(n):
 def test_variant_g_full_size():
     """configs[1]: two-channel 1-s records at 5 MS/s, 2.5 Mchip/s 22-bit code."""
     pc.run_variant_g(pc.CUDA_LIB, 5000000, seeds=[20261017, 20261018], max_batch=2)
+
+
+def test_qpsk_x4_estimator_and_complex_replica():
+    """configs[2]: QPSK, x^4 estimator, 100 kchip/s code (N = 200 000)."""
+    pc.run_qpsk(pc.CUDA_LIB)
+
+
+@pytest.mark.parametrize("n,delay", [(10000, 0.0), (10000, 1.0 / 3.0), (10000, 9999.6), (200000, 4321.7), (200000, 199999.9)])
+def test_variant_k_windows(n, delay):
+    """K variant (fcode=fft(code), P=fcode.*conj(ffty), wrap quirks) through twstft_process_windows."""
+    pc.run_variant_k(pc.CUDA_LIB, n, delay)
+
+
+def test_remote_window_and_negative_offset():
+    pc.run_variant_g(pc.CUDA_LIB, 250000, seeds=[5], window=(80000.0, 120000.0),
+                     overrides=dict(ch1=dict(df=51234.5), ch2=dict(df=49000.25)))
+    pc.run_variant_g(pc.CUDA_LIB, 250000, seeds=[6], window=(-120000.0, -80000.0),
+                     overrides=dict(ch1=dict(df=-51234.5), ch2=dict(df=-43000.0)))
+
+
+def test_host_and_device_entry_points_agree():
+    """twstft_process (host records, staged copies) == twstft_process_device (resident records), 5 records
+    through max_batch 4 (chunked staging + a ragged last batch)."""
+    n = 250000
+    bits, code = pc.make_code(n)
+    recs = np.stack([synth.record_pair(code, s)[0] for s in range(50, 55)])
+    with Correlator(nsamples=n, max_batch=4, lib=pc.CUDA_LIB) as cor:
+        cor.set_code(bits)
+        a = cor.process(recs)
+        dev = cor.to_device(recs)
+        b = cor.process_device(dev, len(recs))
+        cor.device_free(dev)
+    for nm in a.dtype.names:
+        assert np.array_equal(a[nm], b[nm]), nm
+
+
+def test_doppler_bank_small():
+    pc.run_doppler_bank(pc.CUDA_LIB)
+
+
+def test_doppler_bank_64_bins_full_size():
+    """configs[3]: 1-s record at -10 dB correlated over 64 Doppler bins in +/-2 kHz."""
+    res, dfs = pc.run_doppler_bank(pc.CUDA_LIB, n=5000000, nbins=64, span=2000.0, true_df=437.0, seed=20261017,
+                                   check_every=7)
+    assert abs(dfs[int(np.argmax(res["metric"][:, 0]))] - 437.0) <= (dfs[1] - dfs[0])
+
+
+def test_search_df_finds_the_carrier():
+    pc.run_search_df(pc.CUDA_LIB)
