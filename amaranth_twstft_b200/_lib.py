@@ -22,7 +22,7 @@ EXPORTS = [
     "twstft_process_device", "twstft_process_windows", "twstft_estimate_carrier", "twstft_host_alloc",
     "twstft_host_free", "twstft_device_alloc", "twstft_device_free", "twstft_copy_to_device",
     "twstft_copy_to_host", "twstft_synchronize", "twstft_kernel_launches", "twstft_debug_fetch",
-    "twstft_window_bins", "twstft_doppler_bank", "twstft_search_df", "twstft_timer_start", "twstft_timer_stop", "twstft_profile_enable", "twstft_profile_read",
+    "twstft_window_bins", "twstft_doppler_bank", "twstft_search_df", "twstft_estimate_carrier_block", "twstft_timer_start", "twstft_timer_stop", "twstft_profile_enable", "twstft_profile_read",
 ]
 
 
@@ -82,6 +82,7 @@ def load(path=None):
     lib.twstft_estimate_carrier.argtypes = [P, P, C.c_int, C.c_size_t, P, P]
     lib.twstft_doppler_bank.argtypes = [P, P, C.c_int, C.c_size_t, C.c_int64, P, C.c_size_t, C.c_int, P]
     lib.twstft_search_df.argtypes = [P, P, C.c_int, C.c_size_t, C.c_int64, C.c_double, P, P, P]
+    lib.twstft_estimate_carrier_block.argtypes = [P, P, C.c_int, C.c_size_t, C.c_int, P, P]
     lib.twstft_host_alloc.argtypes = [C.c_size_t]
     lib.twstft_host_alloc.restype = P
     lib.twstft_host_free.argtypes = [P]

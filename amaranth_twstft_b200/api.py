@@ -146,12 +146,17 @@ class Correlator:
                     "twstft_process_windows")
         return out
 
-    def estimate_carrier(self, iq):
-        iq, nrec = self._records(iq)
+    def estimate_carrier(self, iq, ls=1):
+        """Carrier offset of every block of ls*N sample instants (ls=2: the 2-s blocks of the K scripts)."""
+        iq = np.ascontiguousarray(iq, dtype=np.int16)
+        per = 2 * self.nch * self.N * ls
+        if iq.size % per:
+            raise ValueError(f"input holds {iq.size} int16, not a multiple of one block ({per})")
+        nrec = iq.size // per
         df = np.zeros((nrec, self.nch))
         bins = np.zeros((nrec, self.nch), dtype=np.int64)
-        self._check(self.lib.twstft_estimate_carrier(self._plan, iq.ctypes.data, 0, nrec, df.ctypes.data,
-                                                     bins.ctypes.data), "twstft_estimate_carrier")
+        self._check(self.lib.twstft_estimate_carrier_block(self._plan, iq.ctypes.data, 0, nrec, int(ls), df.ctypes.data,
+                                                           bins.ctypes.data), "twstft_estimate_carrier_block")
         return df, bins
 
     def doppler_bank(self, iq, dfs, offset=0, sub_mean=True):

@@ -32,7 +32,10 @@ struct ColParams {
     // SRC_RAW
     int nch;               // channels interleaved per sample instant (2: [I1 Q1 I2 Q2], 1: [I Q])
     // (the pre-transform operation is the kernel's OP template parameter:
-    //  0 none, 1 derotate, 2 square, 4 fourth power)
+    //  0 none, 1 derotate, 2 square, 4 fourth power;
+    //  12/14 and 22/24: first radix-2 split of a 2N-sample block for the x^2/x^4 estimator --
+    //  even bins from x^p[n] + x^p[n+N], odd bins from (x^p[n] - x^p[n+N]) * W_2N^n, W from lrow/lcol)
+    i64 half_stride;       // elements between the two halves of a 2N-sample block (OP >= 10)
     int sub_mean;
     const double* sums;    // [lane][2] sum(I), sum(Q) over the window (exact integers)
     const float2* lrow;    // [lane][L]  exp(-j2pi df N2 n1/fs)
@@ -104,14 +107,21 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
         return k;
     }
 
-    static HD float2 pre_op(float2 x, float2 lr)
+    static constexpr int POW = OP % 10;                 // 1 derotate, 2 / 4 power
+    static constexpr int SPLIT = OP / 10;               // 0 none, 1 even half-sum, 2 odd half-difference
+    static constexpr bool USE_LROW = (OP == 1 || SPLIT == 2);
+    static HD float2 power_op(float2 x)
     {
-        if (OP == 1) x = cmul(x, lr);
-        else if (OP >= 2) {
+        if (POW >= 2) {
             x = make_float2(x.x * x.x - x.y * x.y, 2.f * x.x * x.y);
-            if (OP == 4) x = make_float2(x.x * x.x - x.y * x.y, 2.f * x.x * x.y);
+            if (POW == 4) x = make_float2(x.x * x.x - x.y * x.y, 2.f * x.x * x.y);
         }
         return x;
+    }
+    static HD float2 pre_op(float2 x, float2 lr)
+    {
+        if (OP == 1) return cmul(x, lr);
+        return power_op(x);
     }
 
     // stage-0 operands straight from global memory (rows j + NTS*b + m*SP0 of column `col`),
@@ -137,7 +147,15 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
                 for (int m = 0; m < S::R0; m++) {
                     const short2 raw = gsrc[b * bstride + m * mstride];
                     const float2 x = make_float2((float)raw.x - mx, (float)raw.y - my);
-                    r.v[b * S::R0 + m] = pre_op(x, OP == 1 ? lr[S::NTS * b + m * S::SP0] : x);
+                    if (SPLIT == 0) {
+                        r.v[b * S::R0 + m] = pre_op(x, OP == 1 ? lr[S::NTS * b + m * S::SP0] : x);
+                    } else {
+                        const short2 raw2 = gsrc[p.half_stride + b * bstride + m * mstride];
+                        const float2 x2 = make_float2((float)raw2.x - mx, (float)raw2.y - my);
+                        const float2 pa = power_op(x), pb = power_op(x2);
+                        r.v[b * S::R0 + m] = SPLIT == 1 ? cadd(pa, pb)
+                                                        : cmul(csub(pa, pb), lr[S::NTS * b + m * S::SP0]);
+                    }
                 }
         } else if (SRC == SRC_CF32) {
             const float2* gsrc = reinterpret_cast<const float2*>(p.src) + (i64)wk.y * p.N + (i64)j * n2of(p) + col;
@@ -177,7 +195,7 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
             for (int b = 0; b < NBL; b++) {
                 const int jb = j + S::NTS * b;
                 base[b] = cis_cycles(-(double)((i64)n2 * jb) * p.invN);
-                if (SRC == SRC_RAW && OP == 1) base[b] = cmul(base[b], p.lcol[lane * n2of(p) + n2]);
+                if (SRC == SRC_RAW && USE_LROW) base[b] = cmul(base[b], p.lcol[lane * n2of(p) + n2]);
             }
             const i64 bstr = (i64)S::NTS * n2of(p), mstr = (i64)S::NSLAST * n2of(p);
             float2* dj = d + (i64)j * n2of(p);

@@ -33,7 +33,12 @@ struct RowParams {
     int nblk;                // row groups per lane (N1 / RPC)
     // ROW_FWD_ARGMAX
     i64 win_lo, win_hi;      // inclusive window, index s of fftshift(X): s = (k + N/2) mod N
-    u64* part_key;           // [lane][nblk]
+    u64* part_key;           // [lane*key_stride + key_off + rowblk]
+    int key_stride, key_off;
+    // bin k of this transform is bin bmul*k + badd of a transform of nbig points (radix-2 split of a
+    // 2N-sample block, k_col.cuh); the window and the stored index live on that axis.  Default 1, 0, N.
+    int bmul;
+    i64 badd, nbig;
     int oa1, ob1, oa2, ob2;  // k2 ranges that can intersect the window (superset; exact test follows)
     // ROW_FWD_WINMAG
     float* winmag;           // [lane][win_hi - win_lo + 1]  |X|^2 at shifted index s = win_lo + i
@@ -132,7 +137,7 @@ template <class S, int RPC, int MODE> struct KRow {
             // the window; turn that into a per-thread bit mask over the output slots m, then run the
             // exact test on the fftshift'ed index s for those few only.
             u64 best = 0;
-            const i64 half = p.N / 2;
+            const i64 half = p.nbig / 2;
             unsigned mask[NBL];
 #pragma unroll
             for (int b = 0; b < NBL; b++) {
@@ -141,8 +146,8 @@ template <class S, int RPC, int MODE> struct KRow {
             }
             last_stage_visit<S>(j, r.v, [&](int o, float2 x, int b, int m) {
                 if (mask[b] & (1u << m)) {
-                    i64 s = (i64)row + (i64)p.N1 * o + half;
-                    if (s >= p.N) s -= p.N;
+                    i64 s = ((i64)row + (i64)p.N1 * o) * p.bmul + p.badd + half;
+                    if (s >= p.nbig) s -= p.nbig;
                     if (s >= p.win_lo && s <= p.win_hi) {
                         u64 k = make_key(cnorm(x), (unsigned)s);
                         best = k > best ? k : best;
@@ -206,7 +211,7 @@ template <class S, int RPC, int MODE> struct KRow {
         }
         if (HASFIN && PH == NCOMP) {
             if (tid == 0) {
-                if (MODE == ROW_FWD_ARGMAX) p.part_key[wk.lane * p.nblk + wk.rowblk] = r.key;
+                if (MODE == ROW_FWD_ARGMAX) p.part_key[wk.lane * p.key_stride + p.key_off + wk.rowblk] = r.key;
             }
         }
     }

@@ -109,8 +109,8 @@ struct KMean {
 // "+0.25 Hz" grid quirk; claudio_aligned_code_lo_separate.m:103,129), then build the two-level
 // derotation tables exp(-j2pi df n/fs), n = n1*N2 + n2  (godual_ranging.m:17).
 struct DfParams {
-    const u64* part_key;   // [lane][npart]
-    int npart;
+    const u64* part_key;   // [lane*key_stride + i], i < npart
+    int npart, key_stride;
     const double* df_in;   // optional [lane]: skip the estimator (variant K processing(d,k,df))
     double f0, fstep, flast;   // linspace(start, stop, n): start + s*step, last point = stop exactly
     i64 naxis;
@@ -138,7 +138,7 @@ struct KDfFinal {
             u64 best = 0;
             if (!p.df_in)
                 for (int i = tid; i < p.npart; i += NT) {
-                    const u64 k = p.part_key[lane * p.npart + i];
+                    const u64 k = p.part_key[lane * p.key_stride + i];
                     best = k > best ? k : best;
                 }
             r.key = best;

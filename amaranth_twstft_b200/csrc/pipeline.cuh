@@ -51,6 +51,7 @@ public:
     virtual int setup(Backend* be, int max_lanes, int nq) = 0;
     virtual int build_code(const unsigned char* d_bits, int rep, int qpsk, float2 mean, double code_pow) = 0;
     virtual int estimate(const RunArgs& a, const EstimatorCfg& e) = 0;   // -> d_df/d_sbin (+ derotation tables)
+    virtual int estimate_block2(const RunArgs& a, const EstimatorCfg& e) = 0;
     virtual int correlate(const RunArgs& a) = 0;
     virtual int window_spectrum(const RunArgs& a, const EstimatorCfg& e, float* d_win) = 0;
     virtual int bank(const RunArgs& a, int sub_mean, BankRow* d_out) = 0;
@@ -141,7 +142,7 @@ public:
         d_peakpart = dalloc<double>((size_t)lanes * 2 * PEAK_NPTS);
         d_stat = dalloc<double>((size_t)lanes * NCOLTILE_I * 2);
         d_bankpart = dalloc<double>((size_t)lanes * 2 * BANK_NPTS);
-        d_keyrow = dalloc<u64>((size_t)lanes * NROWBLK);
+        d_keyrow = dalloc<u64>((size_t)lanes * NROWBLK * 2);
         d_keycol = dalloc<u64>((size_t)lanes * nq * NCOLTILE_I);
         d_sbin = dalloc<i64>(lanes);
         d_p0 = dalloc<i64>(lanes);
@@ -181,9 +182,10 @@ public:
         be->template launch<KMean>(dim3(nblk, a.nrec, 1), m);
     }
 
-    template <int OP> void col_raw(const RunArgs& a, int sub_mean)
+    template <int OP> void col_raw(const RunArgs& a, int sub_mean, i64 half_stride = 0)
     {
         ColParams c{};
+        c.half_stride = half_stride;
         c.src = a.d_raw; c.dst = d_A; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.invN = 1.0 / (double)N; c.nch = a.nch;
         c.sub_mean = sub_mean; c.sums = d_sums; c.lrow = d_lrow; c.lcol = d_lcol;
         c.rec_stride = a.rec_stride; c.rec_offset = a.d_rec_offset; c.nq = 1;
@@ -197,11 +199,11 @@ public:
         }
     }
 
-    void df_final(const RunArgs& a, const EstimatorCfg* e)
+    void df_final(const RunArgs& a, const EstimatorCfg* e, int npart = NROWBLK)
     {
         const int lanes = a.nrec * a.nch;
         DfParams d{};
-        d.part_key = d_keyrow; d.npart = NROWBLK; d.df_in = e ? nullptr : a.d_df_in;
+        d.part_key = d_keyrow; d.npart = npart; d.key_stride = 2 * NROWBLK; d.df_in = e ? nullptr : a.d_df_in;
         if (e) { d.f0 = e->f0; d.fstep = e->fstep; d.flast = e->flast; d.naxis = e->naxis; d.power = (double)e->power; }
         else { d.power = 1.0; d.naxis = 0; }
         d.fs = a.fs; d.L1 = L1; d.N2 = N2; d.df_out = d_df; d.s_out = d_sbin; d.lrow = d_lrow; d.lcol = d_lcol;
@@ -209,29 +211,67 @@ public:
         be->template launch<KDfFinal>(dim3(d.nsplit, lanes, 1), d);
     }
 
-    // forward transform of x^p and the row-pass parameters of the estimator window
-    RowParams estimator_front(const RunArgs& a, const EstimatorCfg& e)
+    // row-pass parameters of the estimator window; (bmul, badd, nbig) map this transform's bins onto the
+    // axis the window lives on (identity, or one half of the radix-2 split of a 2N-sample block)
+    RowParams estimator_row(const RunArgs& a, const EstimatorCfg& e, int bmul, i64 badd, i64 nbig)
     {
         const int lanes = a.nrec * a.nch;
-        if (e.sub_mean) means(a);
-        have_means = e.sub_mean != 0;
-        if (e.power == 4) col_raw<4>(a, e.sub_mean);
-        else col_raw<2>(a, e.sub_mean);
         RowParams r{};
         r.src = d_A; r.blob = d_blob_r; r.N = N; r.N1 = L1; r.invN = 1.0 / (double)N; r.invM = 1.0 / ((double)nq * (double)N); r.win_lo = e.win_lo; r.win_hi = e.win_hi;
-        r.part_key = d_keyrow; r.nblk = NROWBLK;
+        r.part_key = d_keyrow; r.key_stride = 2 * NROWBLK; r.key_off = 0; r.nblk = NROWBLK;
+        r.bmul = bmul; r.badd = badd; r.nbig = nbig;
         {   // k2 ranges whose bins k = k1 + L1*k2 can intersect the window (bins as signed frequencies)
-            const i64 ka = e.win_lo - N / 2, kb = e.win_hi - N / 2;     // signed bin range [ka, kb]
-            auto lo_of = [&](i64 k) { i64 v = (k - (L1 - 1)) / L1; if ((k - (L1 - 1)) < 0 && (k - (L1 - 1)) % L1) v--; return v; };
+            auto fdiv = [](i64 x, i64 d) { i64 q = x / d; if ((x % d) && ((x < 0) != (d < 0))) q--; return q; };
+            // signed range of this transform's bins: bmul*k + badd in [win_lo - nbig/2, win_hi - nbig/2]
+            const i64 ka = fdiv(e.win_lo - nbig / 2 - badd, bmul) - 1, kb = fdiv(e.win_hi - nbig / 2 - badd, bmul) + 1;
+            auto lo_of = [&](i64 k) { return fdiv(k - (L1 - 1), L1); };
             r.oa1 = 0; r.ob1 = -1; r.oa2 = 0; r.ob2 = -1;
             if (ka >= 0) { r.oa1 = (int)lo_of(ka); r.ob1 = (int)(kb / L1); }
             else if (kb < 0) { r.oa1 = (int)lo_of(ka + N); r.ob1 = (int)((kb + N) / L1); }
             else { r.oa1 = 0; r.ob1 = (int)(kb / L1); r.oa2 = (int)lo_of(ka + N); r.ob2 = N2 - 1; }
             if (r.oa1 < 0) r.oa1 = 0;
             if (r.oa2 < 0) r.oa2 = 0;
+            if (r.ob1 > N2 - 1) r.ob1 = N2 - 1;
         }
         r.nlanes = lanes;
         return r;
+    }
+
+    // forward column transform of x^p and the row-pass parameters of the estimator window
+    RowParams estimator_front(const RunArgs& a, const EstimatorCfg& e)
+    {
+        if (e.sub_mean) means(a);
+        have_means = e.sub_mean != 0;
+        if (e.power == 4) col_raw<4>(a, e.sub_mean);
+        else col_raw<2>(a, e.sub_mean);
+        return estimator_row(a, e, 1, 0, N);
+    }
+
+    // Carrier estimator on blocks of 2N samples (the 2-s blocks of claudio_aligned_code_lo_separate.m:120-129):
+    // first radix-2 split fused into the column-pass loads, two N-point transforms, one arg-max over both.
+    int estimate_block2(const RunArgs& a, const EstimatorCfg& e) override
+    {
+        const int lanes = a.nrec * a.nch;
+        if (lanes > max_lanes) return -2;
+        have_means = false;
+        {   // W_2N^n = exp(-2 pi i n/(2N)) as a "derotation" by fs/(2N) through the two-level tables
+            std::vector<double> half(lanes, a.fs / (2.0 * (double)N));
+            be->h2d(d_df, half.data(), sizeof(double) * lanes);
+            be->sync();
+            RunArgs t = a;
+            t.d_df_in = d_df;
+            df_final(t, nullptr);
+        }
+        typedef KRow<RS, RPC, ROW_FWD_ARGMAX> KR;
+        for (int par = 0; par < 2; par++) {
+            if (e.power == 4) { if (par) col_raw<24>(a, 0, N * a.nch); else col_raw<14>(a, 0, N * a.nch); }
+            else { if (par) col_raw<22>(a, 0, N * a.nch); else col_raw<12>(a, 0, N * a.nch); }
+            RowParams r = estimator_row(a, e, 2, par, 2 * N);
+            r.key_off = par * NROWBLK;
+            be->template launch<KR>(pgrid<KR>((i64)NROWBLK * lanes), r);
+        }
+        df_final(a, &e, 2 * NROWBLK);
+        return be->ok() ? 0 : -1;
     }
 
     int estimate(const RunArgs& a, const EstimatorCfg& e) override

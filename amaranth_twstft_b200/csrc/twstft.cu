@@ -17,6 +17,7 @@ struct twstft_plan {
     Backend be;
     IPipe* pipe = nullptr;
     EstimatorCfg est;
+    EstimatorCfg est2;             // the same estimator on blocks of 2N samples (ls = 2)
     int nch = 2;
     int nq = 3;
     int max_lanes = 0;
@@ -119,6 +120,11 @@ int twstft_plan_create(const twstft_config* cfg, twstft_plan** out)
     e.sub_mean = cfg->est_sub_mean;
     window_bins(e, cfg->win_lo_hz, cfg->win_hi_hz, &e.win_lo, &e.win_hi);
     if (e.win_lo > e.win_hi) return fail(p, TWSTFT_E_ARG, "empty estimator window");
+    EstimatorCfg& e2 = p->est2;     // freq=linspace(-fs/2,fs/2-fs/fs,fs*ls), ls=2 (lo_separate.m:103)
+    e2 = e;
+    e2.naxis = 2 * N;
+    e2.fstep = (e2.flast - e2.f0) / (double)(2 * N - 1);
+    window_bins(e2, cfg->win_lo_hz, cfg->win_hi_hz, &e2.win_lo, &e2.win_hi);
     if (!p->be.ok()) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
     return TWSTFT_OK;
 }
@@ -377,25 +383,31 @@ int twstft_process_windows(twstft_plan* p, const int16_t* iq, int on_device, siz
     return rc;
 }
 
-int twstft_estimate_carrier(twstft_plan* p, const int16_t* iq, int on_device, size_t nrecords,
-                            double* df, int64_t* bins)
+// carrier estimator on nblocks blocks of ls*N sample instants (ls = 1: the window length; ls = 2: the 2-s blocks
+// of the K scripts, N = fs)
+int twstft_estimate_carrier_block(twstft_plan* p, const int16_t* iq, int on_device, size_t nblocks, int ls,
+                                  double* df, int64_t* bins)
 {
-    if (!p || !p->pipe || !iq) return TWSTFT_E_ARG;
+    if (!p || !p->pipe || !iq || (ls != 1 && ls != 2)) return TWSTFT_E_ARG;
+    if (ls == 2 && p->cfg.est_sub_mean) return fail(p, TWSTFT_E_ARG, "ls=2 blocks are estimated on the raw samples (est_sub_mean=0)");
     p->be.use();
     if (!on_device && ensure_raw(p) != 0) return fail(p, TWSTFT_E_NOMEM, "device allocation failed");
     const int B = p->cfg.max_batch;
+    const size_t blk_elems = p->raw_elems_per_rec * ls;
     const short2* src = reinterpret_cast<const short2*>(iq);
-    for (size_t r0 = 0; r0 < nrecords; r0 += B) {
-        const int nb = (int)((nrecords - r0) < (size_t)B ? (nrecords - r0) : B);
-        const short2* d = src + r0 * p->raw_elems_per_rec;
+    const EstimatorCfg& e = ls == 2 ? p->est2 : p->est;
+    for (size_t r0 = 0; r0 < nblocks; r0 += B) {
+        const int nb = (int)((nblocks - r0) < (size_t)B ? (nblocks - r0) : B);
+        const short2* d = src + r0 * blk_elems;
         if (!on_device) {
-            p->be.h2d(p->d_raw, d, sizeof(short2) * p->raw_elems_per_rec * nb);
+            p->be.h2d(p->d_raw, d, sizeof(short2) * blk_elems * nb);
             d = p->d_raw;
         }
         RunArgs a{};
-        a.d_raw = d; a.nrec = nb; a.nch = p->nch; a.rec_stride = (i64)p->raw_elems_per_rec;
+        a.d_raw = d; a.nrec = nb; a.nch = p->nch; a.rec_stride = (i64)blk_elems;
         a.estimate = 1; a.variant = p->cfg.variant; a.ddof = p->cfg.ddof; a.fs = p->cfg.fs; a.d_out = p->d_res;
-        if (p->pipe->estimate(a, p->est) != 0) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
+        const int rc = ls == 2 ? p->pipe->estimate_block2(a, e) : p->pipe->estimate(a, e);
+        if (rc != 0) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
         for (int l = 0; l < nb * p->nch; l++) {
             if (df) p->pipe->debug_fetch(5, l, df + r0 * p->nch + l, sizeof(double));
             if (bins) p->pipe->debug_fetch(7, l, bins + r0 * p->nch + l, sizeof(i64));
@@ -404,6 +416,12 @@ int twstft_estimate_carrier(twstft_plan* p, const int16_t* iq, int on_device, si
         if (!p->be.ok()) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
     }
     return TWSTFT_OK;
+}
+
+int twstft_estimate_carrier(twstft_plan* p, const int16_t* iq, int on_device, size_t nrecords,
+                            double* df, int64_t* bins)
+{
+    return twstft_estimate_carrier_block(p, iq, on_device, nrecords, 1, df, bins);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -74,3 +74,23 @@ def record_pair(code, seed, fs=5e6, ch1=None, ch2=None):
     out[0::4], out[1::4] = quantize(x1)
     out[2::4], out[3::4] = quantize(x2)
     return out, (p1, p2)
+
+
+def stream_single(code, nsamples, seed, delay=0.0, df=0.0, phase=0.3, snr_db=-5.0, fs=5e6, dc=(0.0, 0.0)):
+    """One-channel-per-file recording (rx_multi_samples.cpp:214-215): the code repeats back to back for
+    nsamples sample instants, starting `delay` samples late; [I Q] int16[2*nsamples]."""
+    rng = np.random.default_rng(seed)
+    n = len(code)
+    reps = int(np.ceil((nsamples + n) / n)) + 1
+    s = np.tile(np.asarray(code, dtype=np.complex128), reps)
+    di = int(np.floor(delay)) % n
+    s = s[n - di:n - di + nsamples]
+    t = np.arange(nsamples) / fs
+    s = s * np.exp(1j * (2 * np.pi * df * t + phase))
+    ps = 10.0 ** (snr_db / 10.0)
+    noise = (rng.standard_normal(nsamples) + 1j * rng.standard_normal(nsamples)) / np.sqrt(2.0)
+    x = (np.sqrt(ps) * s + noise) * (3000.0 / np.sqrt((1.0 + ps) / 2.0)) + (dc[0] + 1j * dc[1])
+    i, q = quantize(x)
+    out = np.empty(2 * nsamples, dtype=np.int16)
+    out[0::2], out[1::2] = i, q
+    return out

@@ -15,6 +15,7 @@
  *   twstft_process_windows  processing(d,k,df) / processing(d,df) of variant K   claudio_aligned_code_lo_separate.m:24-77
  *                                                                                 claudio_aligned_code_re_separate.m:48-101
  *   twstft_estimate_carrier  d2=fftshift(abs(fft(d.^2))); [~,df]=max(d2(k))      godual_ranging.m:14-15, lo_separate.m:126-129
+ *   twstft_estimate_carrier_block  the estimator on the 2-s blocks of the K scripts                lo_separate.m:120-129
  *   twstft_doppler_bank  per-bin body of search_df over a grid of offsets (cross-ambiguity)
  *                                                                                 claudio_aligned_code_re_separate.m:33-42
  *   twstft_search_df     k=search_df(d,k,df_threshold)                            claudio_aligned_code_re_separate.m:26-46
@@ -139,6 +140,12 @@ int twstft_doppler_bank(twstft_plan* plan, const int16_t* iq, int iq_on_device, 
  * ncand[ch] = number of candidates.  (The reference runs it on 2-s blocks; here the block is the plan window.) */
 int twstft_search_df(twstft_plan* plan, const int16_t* iq, int iq_on_device, size_t total_instants, int64_t offset,
                      double df_threshold, int64_t* kbon, double* df_found, int32_t* ncand);
+
+/* The same estimator on nblocks blocks of ls*N sample instants.  ls = 2 with N = fs is the 2-s block of
+ * acquisition/claudio_aligned_code_lo_separate.m:120-129 (freq=linspace(-fs/2,fs/2-fs/fs,fs*ls), raw samples
+ * squared, window on that axis): the first radix-2 split of the 2N-point transform is fused into the loads. */
+int twstft_estimate_carrier_block(twstft_plan* plan, const int16_t* iq, int iq_on_device, size_t nblocks, int ls,
+                                  double* df, int64_t* bins);
 
 /* Pinned host memory for the end-to-end path, device memory helpers for device-resident inputs. */
 void* twstft_host_alloc(size_t bytes);

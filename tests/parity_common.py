@@ -143,3 +143,49 @@ def run_search_df(lib, n=250000, true_df=51234.0, seed=8):
     assert ncand[0] == len(tried), (ncand, tried)
     assert kbon[0] == kref, (kbon, kref, tried)
     assert kref > 0 and df[0] == freq[kref - 1] / 2
+
+
+def run_block2_estimator(lib, n=250000, fs=250000.0, seeds=(3, 4), window=(-20000.0, 20000.0)):
+    """Carrier estimator of the K scripts on 2-s blocks (claudio_aligned_code_lo_separate.m:103,120-129):
+    freq=linspace(-fs/2,fs/2-fs/fs,fs*ls), raw samples squared, first max inside the window -> df bit-exact."""
+    rng = np.random.default_rng(1)
+    blocks = []
+    for s in seeds:
+        bits = prn.lfsr_bits(17, 9, n)               # any +/-1 sequence of 2N samples at 1 sample/chip
+        code = 2.0 * bits.astype(np.float64) - 1.0
+        code2 = np.concatenate([code, code])
+        blocks.append(synth.record_single(code2, s, delay=0.0, df=rng.uniform(-9000, 9000), snr_db=-3.0, fs=fs,
+                                          dc=(40.0, -25.0))[0])
+    raw = np.concatenate(blocks)
+    with Correlator(nsamples=n, fs=fs, variant="K", layout="single", window_hz=window, max_batch=2, lib=lib) as cor:
+        df, bins = cor.estimate_carrier(raw, ls=2)
+    freq = np.linspace(-fs / 2, fs / 2 - 1.0, 2 * n)
+    k = oc.window(freq, *window)
+    for i, blk in enumerate(blocks):
+        s, f = oc.carrier_estimate(oc.unpack_single(blk), k, freq)
+        assert bins[i, 0] == s and df[i, 0] == f, (i, bins[i, 0], s, df[i, 0], f)
+
+
+def run_ktrack(lib, fs=250000.0, n=10000, nblocks=2.3, delay=3000.0, df=1234.5, seed=9, max_batch=8):
+    """The K-variant production loop (claudio_aligned_code_lo_separate.m:114-164) through KTracker against
+    its statement-by-statement oracle: df per block bit-exact, same MOVED windows, every window within tolerance."""
+    from amaranth_twstft_b200.ktrack import KTracker
+    from oracle import ktrack as okt
+    bits, code = make_code(n)
+    nsamp = int(nblocks * 2 * fs)
+    raw = synth.stream_single(code, nsamp, seed, delay=delay, df=df, fs=fs, dc=(30.0, -12.0))
+    with KTracker(bits, fs=fs, ls=2, max_batch=max_batch, lib=lib) as kt:
+        got = kt.process_file(raw)
+    ref = okt.lo_separate(raw, code, fs=fs, ls=2)
+    assert not got["status"], got["status"]
+    assert np.array_equal(got["df"], ref["df"]), (got["df"], ref["df"])
+    assert np.array_equal(got["moved"], ref["moved"]) and np.array_equal(got["movedval"], ref["movedval"])
+    assert len(got["indice1"]) == len(ref["indice1"]) and len(ref["moved"]) >= 1
+    assert np.array_equal(got["indice1"], ref["indice1"])
+    assert np.max(np.abs(got["correction1"] - ref["correction1"])) / 3 < TOL_DELAY_SAMPLES
+    assert np.max(np.abs(np.angle(got["xval1"] * np.conj(ref["xval1"])))) < TOL_PHASE_RAD
+    snr = lambda o: 10 * np.log10(o["SNR1r"] + o["SNR1i"])
+    assert np.max(np.abs(snr(got) - snr(ref))) < TOL_SNR_DB
+    assert np.max(np.abs(got["puissance1"] / ref["puissance1"] - 1)) < 1e-3
+    assert abs(got["puissancenoise"] / ref["puissancenoise"] - 1) < 1e-3
+    return got

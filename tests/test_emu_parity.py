@@ -151,3 +151,32 @@ def test_doppler_bank_matches_search_df_body():
 
 def test_search_df_finds_the_carrier():
     pc.run_search_df(pc.EMU_LIB)
+
+
+def test_block2_estimator_equals_2n_point_fft():
+    pc.run_block2_estimator(pc.EMU_LIB)
+    pc.run_block2_estimator(pc.EMU_LIB, window=(100000.0, 120000.0), fs=250000.0 * 2)   # remote window, K-lo OP=0
+
+
+def test_k_tracking_loop_moved_and_dold_carry():
+    got = pc.run_ktrack(pc.EMU_LIB)
+    assert len(got["df"]) == 2 and len(got["indice1"]) >= 98      # 2 blocks of 50 windows, one lost to alignment
+
+
+def test_k_result_file_has_the_reference_schema(tmp_path):
+    """save_mat writes the variables of lo_separate.m:166 with the shapes found in the reference's own result files
+    (experiments/240527/op/localclaudio*.mat.gz, fixture tests/golden/mat_schema.json)."""
+    import scipy.io
+    from amaranth_twstft_b200.ktrack import save_mat
+    got = pc.run_ktrack(pc.EMU_LIB, nblocks=1.1)
+    path = str(tmp_path / "localclaudio_test.mat")
+    save_mat(path, got)
+    m = scipy.io.loadmat(path)
+    schema = json.load(open(os.path.join(G, "mat_schema.json")))
+    ref = next(v for k, v in schema.items() if "localclaudio" in k)
+    for name, meta in ref.items():
+        assert name in m, name
+        assert m[name].ndim == 2 and m[name].shape[0] == 1, (name, m[name].shape)
+        assert str(m[name].dtype) == meta["dtype"], (name, m[name].dtype, meta["dtype"])
+    assert m["indice1"].shape == m["correction1"].shape == m["xval1"].shape == m["SNR1r"].shape
+    assert m["code"].shape == (1, 10000)

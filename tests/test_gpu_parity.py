@@ -91,3 +91,24 @@ def test_doppler_bank_64_bins_full_size():
 
 def test_search_df_finds_the_carrier():
     pc.run_search_df(pc.CUDA_LIB)
+
+
+def test_block2_estimator_production_size():
+    """2-s blocks at 5 MS/s: 10^7-point estimator spectrum through the fused radix-2 split, df bit-exact."""
+    pc.run_block2_estimator(pc.CUDA_LIB, n=5000000, fs=5e6, seeds=(3,))
+
+
+def test_block2_estimator_small():
+    pc.run_block2_estimator(pc.CUDA_LIB)
+
+
+def test_k_tracking_loop_small():
+    pc.run_ktrack(pc.CUDA_LIB)
+
+
+def test_k_tracking_loop_production_shape():
+    """claudio_aligned_code_lo_separate.m configuration: fs = 5 MS/s, 100 kchip/s code (N = 200 000, 25 windows
+    per second), 2-s blocks; 2.2 blocks of a continuous recording with the code 61 234.5 samples late."""
+    got = pc.run_ktrack(pc.CUDA_LIB, fs=5e6, n=200000, nblocks=2.2, delay=61234.5, df=-3210.25, seed=20261017,
+                        max_batch=32)
+    assert len(got["df"]) == 2 and len(got["indice1"]) >= 98
