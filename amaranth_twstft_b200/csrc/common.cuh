@@ -161,6 +161,14 @@ HD void cp_async_wait_all()
 #endif
 }
 
+// Pull one 128-byte line towards L2 ahead of the loads of the next work item (no-op on the host).
+HD void prefetch_l2(const void* g)
+{
+#ifdef __CUDA_ARCH__
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(g));
+#endif
+}
+
 // Order-preserving key for "first maximum": larger value wins, then SMALLER index.
 HD u64 make_key(float v, unsigned idx)
 {

@@ -26,6 +26,10 @@ namespace twstft {
 constexpr int split_kd(int ns)
 {
     if (ns <= 32) return ns;
+    // a half-warp (16 threads, 64-bit words) reads TB[.][jb % KD]: bank-conflict free only if the wrap of
+    // jb % KD falls on a multiple of 16 (ncu: KD = 25 cost 37 % extra shared wavefronts on these loads)
+    if (ns % 32 == 0) return 32;
+    if (ns % 16 == 0) return 16;
     for (int d = 32; d >= 2; d--)
         if (ns % d == 0) return d;
     return 1;
@@ -58,7 +62,12 @@ template <int R0_, int R1_ = 1, int R2_ = 1> struct FFTSpec {
     // stage-0 twiddle tables: root index jb in [0, SP0)
     static constexpr int KD0 = split_kd(SP0), KH0 = SP0 / KD0;
     typedef Seeds<R0, false> SD0;          // stage-0 twiddles w = W_L^jb, jb in [0, SP0)
-    typedef Seeds<R1, false> SD1;                // middle-stage twiddles w = W_{R1 R2}^i2, i2 in [0, R2)
+#ifndef TWSTFT_SD1_FULL
+#define TWSTFT_SD1_FULL 1
+#endif
+    // middle-stage twiddles w = W_{R1 R2}^i2, i2 in [0, R2): the table is small (R1*R2 entries), so every
+    // power is tabulated and no seed products are formed (12 complex multiplies less per radix-20 butterfly)
+    typedef Seeds<R1, TWSTFT_SD1_FULL != 0> SD1;
     static constexpr int NSEED0 = SD0::N, NSEED1 = SD1::N;
     static constexpr int OFF_B0 = 0;
     static constexpr int OFF_A0 = OFF_B0 + (NSTAGE > 1 ? NSEED0 * KD0 : 0);
@@ -158,6 +167,24 @@ template <class S, class Acc> HD void dif_stage0(int j, float2* v, const float2*
     }
 }
 
+// Middle-stage butterflies are indexed by (k0, i2) and touch the words k0*bstride + i2 + m*R2.  With
+// jb -> (jb / R2, jb % R2) three half-warps out of four straddle two blocks k0 and, the block stride being
+// odd for the sake of the last stage, collide in one bank (ncu: 37.5 % excess wavefronts on every load and
+// store of this stage).  For the 20 x 20 grid of the length-8000 rows the butterflies are dealt out in
+// tiles of 16 instead: 20 tiles (one k0, i2 = 0..15), 4 tiles (one i2 >= 16, k0 = 0..15: odd stride ->
+// 16 distinct banks) and one 4 x 4 tile in the corner (the only one left with a 2-way conflict).
+template <class S> HD void mid_map(int jb, int& k0, int& i2)
+{
+    if (S::R0 == 20 && S::R2 == 20) {
+        if (jb < 320) { k0 = jb >> 4; i2 = jb & 15; }
+        else if (jb < 384) { const int u = jb - 320; i2 = 16 + (u >> 4); k0 = u & 15; }
+        else { const int u = jb - 384; k0 = 16 + (u >> 2); i2 = 16 + (u & 3); }
+    } else {
+        k0 = jb / S::R2;
+        i2 = jb % S::R2;
+    }
+}
+
 // ---- middle stage (3-stage transforms): digit i1, in place ------------------------------------
 template <class S, class Acc> HD void dif_stage_mid(int j, float2* v, const float2* tw, const Acc& acc)
 {
@@ -165,7 +192,8 @@ template <class S, class Acc> HD void dif_stage_mid(int j, float2* v, const floa
 #pragma unroll
     for (int b = 0; b < NB; b++) {
         const int jb = j + S::NTS * b;
-        const int k0 = jb / S::R2, i2 = jb % S::R2;
+        int k0, i2;
+        mid_map<S>(jb, k0, i2);
         float2* vb = v + b * R;
         float2* p = acc.at(k0, i2);
 #pragma unroll

@@ -204,6 +204,12 @@ template <class S, int RPC, int MODE> struct KRow {
             dif_stage0<S>(j, r.v, sm, acc);
             if (S::NSTAGE == 1) epilogue(p, wk, rl, j, r, gtab);
         }
+        if (S::NSTAGE >= 2 && PH == 1 && it + 1 < nit) {   // next item's rows towards L2
+            const Work nx = work_of(p, blk, it + 1);
+            const char* a = reinterpret_cast<const char*>(p.src + nx.lane * p.N + (i64)nx.rowblk * RPC * S::L);
+            constexpr int NLINE = (int)((size_t)RPC * S::L * sizeof(float2) / 128);
+            for (int l = tid; l < NLINE; l += NTA) prefetch_l2(a + (size_t)l * 128);
+        }
         if (S::NSTAGE == 3 && PH == 1) dif_stage_mid<S>(j, r.v, sm, acc);
         if (S::NSTAGE >= 2 && PH == S::NSTAGE - 1) {
             dif_stage_last<S>(j, r.v, acc);

@@ -190,6 +190,17 @@ template <class S, int RPC, int NQ> struct KRowCorr {
                 dif_stage0<S>(j, r.v, sm, acc);
             }
         }
+        if (F == (NQ > 1 ? 2 : 1) && ST == 0 && it + 1 < nit) {
+            // next item's spectrum rows and code rows towards L2 while this one is still being transformed
+            const Work nx = work_of(p, blk, it + 1);
+            const char* a = reinterpret_cast<const char*>(p.src + nx.lane * p.N + (i64)nx.rowblk * RPC * S::L);
+            const char* c = reinterpret_cast<const char*>(p.code + (i64)nx.rowblk * RPC * S::L);
+            constexpr int NLINE = (int)((size_t)RPC * S::L * sizeof(float2) / 128);
+            for (int l = tid; l < NLINE; l += NT) {
+                prefetch_l2(a + (size_t)l * 128);
+                prefetch_l2(c + (size_t)l * 128);
+            }
+        }
         if (F > 0 && ST == 0) {
             constexpr int q = F - 1;
             if (q > 0) fetch(r);                          // q == 0: P is still in v
