@@ -154,7 +154,7 @@ struct KDfFinal {
             }
             if (blk.x == 0 && tid == 0) {
                 p.df_out[lane] = df;
-                p.s_out[lane] = s;
+                if (p.s_out) p.s_out[lane] = s;
             }
             const int tot = p.L1 + p.N2;
             for (int e = blk.x * NT + tid; e < tot; e += p.nsplit * NT) {
@@ -162,6 +162,111 @@ struct KDfFinal {
                 else p.lcol[lane * p.N2 + (e - p.L1)] = cis_cycles(-df * ((double)(e - p.L1) / p.fs));
             }
         }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Fine-frequency refinement: experiments/221219_twoway/processing/godual_ranging.py:26-30
+// (= the block commented out at processing/Octave/godual_ranging.m:19-24):
+//     a = polyfit([1:10:fs/3]/fs, conv(angle(y(1:10:fs/3)), ones(100,1)/100)(50:end-50), 1)
+//     dfleftover = a(1)/2/pi ;  y = y .* exp(-j*2*pi*dfleftover*temps) ;  df += dfleftover
+// KFineAngle evaluates angle(y) of every `step`-th derotated, mean-removed sample in fp64 (the angles are
+// NOT unwrapped by the reference, so a sample that lands on the other side of +/-pi would move the fit:
+// fp64 keeps that as unlikely as in numpy); KFineFit forms the centred least-squares numerator
+// sum (i - c) s_i of the 100-tap smoothed angles s_i (the regressor is equally spaced, so the slope is
+// fs/step * sum (i-c) s_i / (M (M^2-1)/12)); KFineFinal adds the slope/2pi to df.
+struct FineParams {
+    const short2* src;
+    int nch;
+    i64 rec_stride;
+    const i64* rec_offset;
+    const double* sums;    // [lane][2] window sums (means = sums * invN)
+    double invN;
+    double fs;
+    int M, step, taps;     // M samples at stride `step`, moving average of `taps` (100)
+    double* ang;           // [lane][M]
+    double* part;          // [lane][nsplit]
+    int nsplit;
+    double* df;            // [lane] in: coarse df, out (KFineFinal): df + dfleftover
+};
+struct KFineAngle {
+    typedef FineParams Params;
+    static const char* name() { return "fine_angle"; }
+    static constexpr bool PERSISTENT = false;
+    static constexpr int NT = 256, MINB = 4, NPH = 1, NSUM = 1;
+    struct Regs { u64 key; double dsum[NSUM]; };
+    static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }
+    static HD constexpr int sync_after(int) { return SYNC_BARRIER; }
+    template <int PH> static HD void phase(const Params& p, const Blk& blk, int tid, Regs&, unsigned char*)
+    {
+        const i64 lane = blk.y;
+        const int rec = (int)(lane / p.nch), ch = (int)(lane % p.nch);
+        const i64 i = (i64)blk.x * NT + tid;
+        if (i >= p.M) return;
+        const i64 base = p.rec_offset ? p.rec_offset[rec] : (i64)rec * p.rec_stride;
+        const i64 n = i * p.step;
+        const short2 raw = p.src[base + n * p.nch + ch];
+        const double x = (double)raw.x - p.sums[lane * 2] * p.invN, y = (double)raw.y - p.sums[lane * 2 + 1] * p.invN;
+        const double2 lo = cis_cycles_d(-p.df[lane] * ((double)n / p.fs));
+        p.ang[lane * p.M + i] = atan2(x * lo.y + y * lo.x, x * lo.x - y * lo.y);
+    }
+};
+struct KFineFit {
+    typedef FineParams Params;
+    static const char* name() { return "fine_fit"; }
+    static constexpr bool PERSISTENT = false;
+    static constexpr int NT = 256, MINB = 4, NPH = 2, NSUM = 1;
+    struct Regs { u64 key; double dsum[NSUM]; };
+    static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }
+    static HD constexpr int sync_after(int) { return SYNC_SUMD; }
+    template <int PH> static HD void phase(const Params& p, const Blk& blk, int tid, Regs& r, unsigned char*)
+    {
+        const i64 lane = blk.y;
+        if (PH == 0) {
+            // thread t of CTA x owns the contiguous run [i0, i1) of smoothed samples: one window sum, then slide
+            const i64 nthr = (i64)p.nsplit * NT, per = (p.M + nthr - 1) / nthr;
+            const i64 i0 = ((i64)blk.x * NT + tid) * per;
+            i64 i1 = i0 + per;
+            if (i1 > p.M) i1 = p.M;
+            const double* a = p.ang + lane * p.M;
+            const int before = p.taps / 2, after = p.taps - before - 1;     // window [i-50, i+49]
+            const double c = 0.5 * (double)(p.M - 1), w = 1.0 / (double)p.taps;
+            double acc = 0.0, win = 0.0;
+            for (i64 i = i0; i < i1; i++) {
+                if (i == i0 || ((i - i0) & 63) == 0) {                      // fresh sum now and then: no drift
+                    win = 0.0;
+                    const i64 lo = i - before < 0 ? 0 : i - before, hi = i + after > p.M - 1 ? p.M - 1 : i + after;
+                    for (i64 l = lo; l <= hi; l++) win += a[l];
+                } else {
+                    if (i + after <= p.M - 1) win += a[i + after];
+                    if (i - before - 1 >= 0) win -= a[i - before - 1];
+                }
+                acc += ((double)i - c) * (win * w);
+            }
+            r.key = 0;
+            r.dsum[0] = acc;
+        } else if (tid == 0) {
+            p.part[lane * p.nsplit + blk.x] = r.dsum[0];
+        }
+    }
+};
+struct KFineFinal {
+    typedef FineParams Params;
+    static const char* name() { return "fine_final"; }
+    static constexpr bool PERSISTENT = false;
+    static constexpr int NT = 32, MINB = 4, NPH = 1, NSUM = 1;
+    struct Regs { u64 key; double dsum[NSUM]; };
+    static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }
+    static HD constexpr int sync_after(int) { return SYNC_BARRIER; }
+    template <int PH> static HD void phase(const Params& p, const Blk& blk, int tid, Regs&, unsigned char*)
+    {
+        if (tid != 0) return;
+        const i64 lane = blk.y;
+        double num = 0.0;
+        for (int i = 0; i < p.nsplit; i++) num += p.part[lane * p.nsplit + i];
+        const double M = (double)p.M;
+        const double slope = (p.fs / (double)p.step) * num / (M * (M * M - 1.0) / 12.0);   // rad / s
+        p.df[lane] += slope / 6.283185307179586476925287;
     }
 };
 

@@ -52,6 +52,7 @@ public:
     virtual int build_code(const unsigned char* d_bits, int rep, int qpsk, float2 mean, double code_pow) = 0;
     virtual int estimate(const RunArgs& a, const EstimatorCfg& e) = 0;   // -> d_df/d_sbin (+ derotation tables)
     virtual int estimate_block2(const RunArgs& a, const EstimatorCfg& e) = 0;
+    virtual int fine_frequency(const RunArgs& a) = 0;   // A10: d_df += dfleftover, derotation tables rebuilt
     virtual int correlate(const RunArgs& a) = 0;
     virtual int window_spectrum(const RunArgs& a, const EstimatorCfg& e, float* d_win) = 0;
     virtual int bank(const RunArgs& a, int sub_mean, BankRow* d_out) = 0;
@@ -84,7 +85,7 @@ public:
     {
         if (!be) return;
         void* all[] = {d_blob_c, d_blob_r, d_code, d_qconst, d_A, d_B, d_sums, d_energy, d_df, d_peakpart,
-                       d_keyrow, d_keycol, d_sbin, d_p0, d_y0, d_lrow, d_lcol, d_stat, d_bankpart};
+                       d_keyrow, d_keycol, d_sbin, d_p0, d_y0, d_lrow, d_lcol, d_stat, d_bankpart, d_ang, d_finepart};
         for (void* p : all) be->free(p);
     }
     i64 size() const override { return N; }
@@ -199,14 +200,14 @@ public:
         }
     }
 
-    void df_final(const RunArgs& a, const EstimatorCfg* e, int npart = NROWBLK)
+    void df_final(const RunArgs& a, const EstimatorCfg* e, int npart = NROWBLK, bool keep_sbin = false)
     {
         const int lanes = a.nrec * a.nch;
         DfParams d{};
         d.part_key = d_keyrow; d.npart = npart; d.key_stride = 2 * NROWBLK; d.df_in = e ? nullptr : a.d_df_in;
         if (e) { d.f0 = e->f0; d.fstep = e->fstep; d.flast = e->flast; d.naxis = e->naxis; d.power = (double)e->power; }
         else { d.power = 1.0; d.naxis = 0; }
-        d.fs = a.fs; d.L1 = L1; d.N2 = N2; d.df_out = d_df; d.s_out = d_sbin; d.lrow = d_lrow; d.lcol = d_lcol;
+        d.fs = a.fs; d.L1 = L1; d.N2 = N2; d.df_out = d_df; d.s_out = keep_sbin ? nullptr : d_sbin; d.lrow = d_lrow; d.lcol = d_lcol;
         d.nsplit = 8;
         be->template launch<KDfFinal>(dim3(d.nsplit, lanes, 1), d);
     }
@@ -282,6 +283,41 @@ public:
         typedef KRow<RS, RPC, ROW_FWD_ARGMAX> KR;
         be->template launch<KR>(pgrid<KR>((i64)NROWBLK * lanes), r);
         df_final(a, &e);
+        return be->ok() ? 0 : -1;
+    }
+
+    // Fine-frequency refinement after estimate(): needs the window means (left in d_sums by estimate() when the
+    // estimator removes them, computed here otherwise) and the coarse df in d_df.
+    double* d_ang = nullptr;
+    double* d_finepart = nullptr;
+    int fine_M = 0;
+    static constexpr int FINE_SPLIT = 8;
+    int fine_frequency(const RunArgs& a) override
+    {
+        const int lanes = a.nrec * a.nch;
+        if (lanes > max_lanes) return -2;
+        const i64 third = (i64)floor(a.fs) / 3;                    // fs//3
+        const int step = 10;
+        const i64 My = ((third < N ? third : N) + step - 1) / step;   // len(y[0:fs//3:10])
+        const i64 Mt = (third - 1 + step - 1) / step;                 // len(arange(1, fs//3, 10))
+        if (My != Mt || My < 2) return -3;                            // numpy raises in the reference
+        if (!d_ang || fine_M != (int)My) {
+            be->free(d_ang); be->free(d_finepart);
+            d_ang = dalloc<double>((size_t)max_lanes * My);
+            d_finepart = dalloc<double>((size_t)max_lanes * FINE_SPLIT);
+            fine_M = (int)My;
+        }
+        if (!have_means) { means(a); have_means = true; }
+        FineParams f{};
+        f.src = a.d_raw; f.nch = a.nch; f.rec_stride = a.rec_stride; f.rec_offset = a.d_rec_offset; f.sums = d_sums;
+        f.invN = 1.0 / (double)N; f.fs = a.fs; f.M = (int)My; f.step = step; f.taps = 100; f.ang = d_ang;
+        f.part = d_finepart; f.nsplit = FINE_SPLIT; f.df = d_df;
+        be->template launch<KFineAngle>(dim3((unsigned)((My + KFineAngle::NT - 1) / KFineAngle::NT), lanes, 1), f);
+        be->template launch<KFineFit>(dim3(FINE_SPLIT, lanes, 1), f);
+        be->template launch<KFineFinal>(dim3(1, lanes, 1), f);
+        RunArgs t = a;
+        t.d_df_in = d_df;
+        df_final(t, nullptr, NROWBLK, true);                          // tables for df + dfleftover, carrier bin kept
         return be->ok() ? 0 : -1;
     }
 

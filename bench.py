@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 N = 5000000
 FS = 5e6
 CODE = (22, 3, 2500000)          # bitlen, taps, noiselen (experiments/221207_twoway_codes/codes/noiselen2500000_bitlen22_taps03)
-RECORDS_PER_STEP = 8
+RECORDS_PER_STEP = 16
 METRIC = "two-channel 1-s 5 MS/s records correlated per second"
 UNIT = "records/s"
 SURVEY_BYTES_PER_RECORD = 1.4e9  # 140*N bytes per channel, two channels
@@ -51,50 +51,74 @@ def make_records(code, seeds):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and clock-event (throttle) reasons sampled through NVML every millisecond by a thread, ONLY between
+    begin() and end() -- i.e. during the timed region (B200_PROFILING.md clocks line; nvidia-smi -lms cannot sample a
+    region that lasts tens of milliseconds).  Falls back to one nvidia-smi query if NVML is unavailable."""
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.h, self.nv = index, None, None
+        self.sm, self.reasons, self.smax = [], set(), None
+        self.on = threading.Event()
+        self.quit = threading.Event()
+        self.thread = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml as nv
+            nv.nvmlInit()
+            idx = self.index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                idx = int(vis.split(",")[self.index])
+            self.h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.smax = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.nv = nv
+            self.thread = threading.Thread(target=self._run, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            self.nv = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _sample(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        for name, bit in (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                          ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                          ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                          ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _run(self):
+        while not self.quit.is_set():
+            if self.on.wait(0.05):
+                try:
+                    self._sample()
+                except Exception:
+                    pass
+                time.sleep(0.001)
+
+    def begin(self):
+        self.on.set()
+
+    def end(self):
+        self.on.clear()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], None, set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
+        self.quit.set()
+        if self.nv is None:
             try:
-                sm.append(float(f[1]))
-                smax = float(f[2])
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20).stdout
+                f = [float(x) for x in out.strip().split(",")]
+                return {"sm_mhz": f[0], "sm_max_mhz": f[1], "reasons": [], "samples": 1,
+                        "how": "one nvidia-smi query after the timed region (NVML unavailable)"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
+        self.thread.join(timeout=1.0)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "how": "NVML, 1 ms period, sampled only inside the timed region"}
 
 
 def oracle_record(raw, code):
@@ -200,19 +224,21 @@ def main():
         host[i * r.size:(i + 1) * r.size] = r
     dev = cor.to_device(host)
 
-    sampler = ClockSampler(local)     # started before the warm-up so that nvidia-smi is up during the timed steps
+    sampler = ClockSampler(local)
     sampler.start()
     for _ in range(max(args.warmup, 3)):
         res = cor.process_device(dev, R)
+    cor.synchronize()
     barrier()
     l0 = cor.kernel_launches
+    sampler.begin()
     cor.timer_start()
     for _ in range(args.steps):
         res = cor.process_device(dev, R)
-    ms = cor.timer_stop()
+    ms = cor.timer_stop()             # records the stop event and synchronises the plan's stream
+    sampler.end()
     launches = cor.kernel_launches - l0
     barrier()
-    clocks = sampler.stop()
     ms = max_over_ranks(ms)
     value = world * R * args.steps / (ms * 1e-3)
 
@@ -220,11 +246,13 @@ def main():
     for _ in range(2):
         cor.process(host)
     barrier()
+    sampler.begin()
     cor.timer_start()
     e2e_steps = max(3, args.steps // 2)
     for _ in range(e2e_steps):
         res_e2e = cor.process(host)
     ms_e2e = max_over_ranks(cor.timer_stop())
+    clocks = sampler.stop()
     e2e_value = world * R * e2e_steps / (ms_e2e * 1e-3)
     barrier()
 

@@ -74,6 +74,10 @@ typedef struct twstft_config {
     int ddof;           /* 1: Octave var (n-1), 0: numpy/C++ var (n) */
     int max_batch;      /* records (or windows) per device batch */
     int device_id;
+    int fine_freq;      /* 1: fine-frequency refinement before the correlation (twstft_process only): slope of the
+                           100-tap smoothed angle(y(1:10:fs/3)), df += slope/2pi --
+                           experiments/221219_twoway/processing/godual_ranging.py:26-30 (commented out at
+                           processing/Octave/godual_ranging.m:19-24); 0 (default): off */
 } twstft_config;
 
 /* One row of the reference's result variables, per channel and record (all doubles). */

@@ -75,6 +75,47 @@ def run_variant_g(lib, n, seeds, fs=5e6, window=(-20000.0, 20000.0), max_batch=2
     return res
 
 
+def run_ref_py_golden(lib, name):
+    """The library with fine_freq=1, ddof=0 against the committed outputs of the reference's OWN numpy correlator
+    (experiments/221219_twoway/processing/godual_ranging.py `processing()`, run unmodified by tools/make_golden.py)
+    on the same seeded records; phase (not returned by that function) against the oracle."""
+    import hashlib
+    import json
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", f"ref_py_{name}.json")))
+    fs = g["fs"]
+    bits = prn.lfsr_bits(g["bitlen"], g["taps"], g["noiselen"])
+    code = oc.code_bpsk(bits)
+    n = len(code)
+    recs = []
+    for rec in g["records"]:
+        raw, _ = synth.record_pair(code, rec["seed"], fs=fs, ch1=rec["ch1_override"])
+        assert hashlib.sha256(raw.tobytes()).hexdigest() == rec["sha256"], "synthetic generator drifted"
+        recs.append(raw)
+    w = g["window_hz"]
+    with Correlator(nsamples=n, fs=fs, window_hz=(-w, w), ddof=0, fine_freq=True, max_batch=2, lib=lib) as cor:
+        cor.set_code(bits)
+        res = cor.process(np.stack(recs))
+    freq = oc.freq_axis_G(fs, n)
+    k = oc.window(freq, -w, w)
+    fcode = oc.fcode_G(code)
+    for i, rec in enumerate(g["records"]):
+        orc = oc.record_G(recs[i], k, freq, fcode, code, fs=fs, fine_freq=True, ddof=0) if n <= 200000 or i == 0 else None
+        for ch in (1, 2):
+            r, ref = res[i, ch - 1], rec["out"][str(ch)]
+            where = f"{name} seed={rec['seed']} ch{ch}"
+            assert int(r["indice"]) - 1 == ref["indice"], f"{where}: peak index"          # golden is 0-based
+            assert abs(r["correction"] - ref["correction"]) / 3.0 < TOL_DELAY_SAMPLES, f"{where}: correction"
+            # dfleftover moves the phase at the peak by ~pi*T*d(df): 1e-5 Hz keeps it far inside 1e-4 rad
+            assert abs(r["df"] - ref["df"]) < 1e-5 * fs / 5e6 + 1e-9 * abs(ref["df"]), f"{where}: df {r['df']} vs {ref['df']}"
+            assert abs(snr_db(r) - 10 * np.log10(ref["SNRr"] + ref["SNRi"])) < TOL_SNR_DB, f"{where}: SNR"
+            for nm in ("puissance", "puissancecode", "puissancenoise"):
+                assert abs(r[nm] / ref[nm] - 1) < 1e-3, f"{where}: {nm}"
+            if orc is not None:
+                xv = complex(r["xval_re"], r["xval_im"])
+                assert abs(np.angle(xv * np.conj(orc[ch]["xval"]))) < TOL_PHASE_RAD, f"{where}: phase"
+    return res
+
+
 def run_qpsk(lib, n=200000, seeds=(41, 42), window=(-40000.0, 40000.0)):
     """configs[2]: QPSK record, x^4 carrier estimator (df=freq/4, Doc/07_Demodulation.md:60-63), replica
     (codei+j*codeq)-mean of experiments/220822_qpsk_vs_bpsk/goqpsk.m:10-16, 100 kchip code (17 bits, taps 9/15)."""

@@ -24,6 +24,12 @@ def test_variant_g(n):
     pc.run_variant_g(pc.EMU_LIB, n, seeds=[11, 12, 13])
 
 
+@pytest.mark.parametrize("name", ["n1e4", "n2e5"])
+def test_fine_frequency_against_reference_python_outputs(name):
+    """A10 + the whole G path against tests/golden/ref_py_*.json (outputs of the reference's own numpy code)."""
+    pc.run_ref_py_golden(pc.EMU_LIB, name)
+
+
 def test_variant_g_1e6():
     pc.run_variant_g(pc.EMU_LIB, 1000000, seeds=[11])
 

@@ -44,6 +44,13 @@ def test_variant_g_full_size():
     pc.run_variant_g(pc.CUDA_LIB, 5000000, seeds=[20261017, 20261018], max_batch=2)
 
 
+@pytest.mark.parametrize("name", ["n1e4", "n2e5", "n5e6"])
+def test_against_reference_python_outputs(name):
+    """fine_freq=1, ddof=0: CUDA results against the committed outputs of the reference's own
+    experiments/221219_twoway/processing/godual_ranging.py on the same seeded records (n5e6 = configs[1] shape)."""
+    pc.run_ref_py_golden(pc.CUDA_LIB, name)
+
+
 def test_qpsk_x4_estimator_and_complex_replica():
     """configs[2]: QPSK, x^4 estimator, 100 kchip/s code (N = 200 000)."""
     pc.run_qpsk(pc.CUDA_LIB)
