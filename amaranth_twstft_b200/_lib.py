@@ -83,6 +83,8 @@ def load(path=None):
     lib.twstft_doppler_bank.argtypes = [P, P, C.c_int, C.c_size_t, C.c_int64, P, C.c_size_t, C.c_int, P]
     lib.twstft_search_df.argtypes = [P, P, C.c_int, C.c_size_t, C.c_int64, C.c_double, P, P, P]
     lib.twstft_estimate_carrier_block.argtypes = [P, P, C.c_int, C.c_size_t, C.c_int, P, P]
+    lib.twstft_search_df_block.argtypes = [P, P, P, C.c_int, C.c_int, C.c_double, P, P, P]
+    lib.twstft_estimate_bins.argtypes = [P, P, C.c_int, C.c_size_t, C.c_int64, C.c_int, P]
     lib.twstft_host_alloc.argtypes = [C.c_size_t]
     lib.twstft_host_alloc.restype = P
     lib.twstft_host_free.argtypes = [P]

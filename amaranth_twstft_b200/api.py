@@ -182,6 +182,36 @@ class Correlator:
                     "twstft_search_df")
         return kbon, df, ncand
 
+    def search_df_block(self, cor, iq, ls=2, df_threshold=20.0, on_device=False):
+        """search_df as the re/ranging scripts call it: spectrum of the whole block of ls*N sample instants (this plan),
+        candidates tested on the first cor.N instants against cor's code.  Returns (kbon, df, ncand) per channel."""
+        kbon = np.zeros(self.nch, dtype=np.int64)
+        df = np.zeros(self.nch)
+        ncand = np.zeros(self.nch, dtype=np.int32)
+        if on_device:
+            ptr = iq
+        else:
+            iq = np.ascontiguousarray(iq, dtype=np.int16)
+            if iq.size != 2 * self.nch * self.N * ls:
+                raise ValueError("search_df_block takes exactly one block of ls*N sample instants")
+            ptr = iq.ctypes.data
+        self._check(self.lib.twstft_search_df_block(self._plan, cor._plan, ptr, int(on_device), int(ls),
+                                                    float(df_threshold), kbon.ctypes.data, df.ctypes.data,
+                                                    ncand.ctypes.data), "twstft_search_df_block")
+        return kbon, df, ncand
+
+    def estimate_bins(self, iq, s_first, nbins, on_device=False, ninstants=None):
+        """|fft(x.^p)| at the 0-based fftshift'ed positions s_first..s_first+nbins-1 of a buffer of any length."""
+        mag = np.zeros((self.nch, nbins))
+        if on_device:
+            ptr, n = iq, int(ninstants)
+        else:
+            iq = np.ascontiguousarray(iq, dtype=np.int16)
+            ptr, n = iq.ctypes.data, iq.size // (2 * self.nch)
+        self._check(self.lib.twstft_estimate_bins(self._plan, ptr, int(on_device), n, int(s_first), int(nbins),
+                                                  mag.ctypes.data), "twstft_estimate_bins")
+        return mag
+
     # ------------------------------------------------------------------ timing (CUDA events on the plan's stream)
     def synchronize(self):
         self._check(self.lib.twstft_synchronize(self._plan), "twstft_synchronize")

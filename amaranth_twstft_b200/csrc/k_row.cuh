@@ -156,7 +156,7 @@ template <class S, int RPC, int MODE> struct KRow {
             });
             r.key = best;
         } else {  // ROW_FWD_WINMAG: same window test as the arg-max, values stored instead of reduced
-            const i64 half = p.N / 2;
+            const i64 half = p.nbig / 2;
             const i64 wlen = p.win_hi - p.win_lo + 1;
             float* wm = p.winmag + lane * wlen;
             unsigned mask[NBL];
@@ -167,8 +167,8 @@ template <class S, int RPC, int MODE> struct KRow {
             }
             last_stage_visit<S>(j, r.v, [&](int o, float2 x, int b, int m) {
                 if (mask[b] & (1u << m)) {
-                    i64 s = (i64)row + (i64)p.N1 * o + half;
-                    if (s >= p.N) s -= p.N;
+                    i64 s = ((i64)row + (i64)p.N1 * o) * p.bmul + p.badd + half;
+                    if (s >= p.nbig) s -= p.nbig;
                     if (s >= p.win_lo && s <= p.win_hi) wm[s - p.win_lo] = cnorm(x);
                 }
             });

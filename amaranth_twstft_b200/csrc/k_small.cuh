@@ -104,6 +104,69 @@ struct KMean {
 };
 
 // ------------------------------------------------------------------------------------------------
+// KBinsDFT: a few ADJACENT bins of fft(x.^p) over a buffer of ANY length, evaluated directly in fp64.
+// The re/ranging production scripts re-estimate the carrier on d=[dold ; block] -- a transform whose
+// length changes from block to block and is not 2/5-smooth -- but look at seven bins only:
+//   d2=fftshift(abs(fft(d(1:end).^2))); [~,df]=max(d2(kbon-3:kbon+3))
+//   acquisition/claudio_aligned_code_re_separate.m:167-168 (= ..._ranging_separate.m)
+// X[k0+i] = sum_n x[n]^p W^{(k0+i) n}, W = exp(-2 pi i/L): per sample one exactly reduced phase
+// (k0*n mod L in 64-bit integers), one step phase and nb-1 complex multiplies; one pass over the buffer.
+struct BinsParams {
+    const short2* src;     // [ninst][nch] complex int16
+    i64 ninst;             // transform length L (sample instants)
+    int nch;
+    int power;             // 2 or 4
+    i64 k0;                // first bin, 0 <= k0 < L; bins (k0+i) mod L
+    int nb;                // bins, <= KBinsDFT::MAXB
+    double* part;          // [ch][nblk][2*MAXB] partial sums (re, im per bin)
+    int nblk;
+};
+struct KBinsDFT {
+    typedef BinsParams Params;
+    static const char* name() { return "bins_dft"; }
+    static constexpr bool PERSISTENT = false;
+    static constexpr int MAXB = 8;
+    static constexpr int NT = 256, MINB = 2, NPH = 2, NSUM = 2 * MAXB;
+    struct Regs { u64 key; double dsum[NSUM]; };
+    static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }
+    static HD constexpr int sync_after(int) { return SYNC_SUMD; }
+    template <int PH> static HD void phase(const Params& p, const Blk& blk, int tid, Regs& r, unsigned char*)
+    {
+        if (PH == 0) {
+            double ar[MAXB], ai[MAXB];
+#pragma unroll
+            for (int i = 0; i < MAXB; i++) ar[i] = ai[i] = 0.0;
+            const int ch = blk.y;
+            const double invL = 1.0 / (double)p.ninst;
+            const i64 stride = (i64)p.nblk * NT;
+            for (i64 n = (i64)blk.x * NT + tid; n < p.ninst; n += stride) {
+                const short2 v = p.src[n * p.nch + ch];
+                const double xr = (double)v.x, xi = (double)v.y;
+                double zr = xr * xr - xi * xi, zi = 2.0 * xr * xi;          // x^2 (exact: |x| < 2^15)
+                if (p.power == 4) { const double t = zr * zr - zi * zi; zi = 2.0 * zr * zi; zr = t; }
+                const i64 ph = (i64)(((u64)p.k0 * (u64)n) % (u64)p.ninst);  // k0*n < 2^63 for L < 2^31
+                double2 w = cis_cycles_d(-(double)ph * invL);
+                const double2 ws = cis_cycles_d(-(double)n * invL);
+#pragma unroll
+                for (int i = 0; i < MAXB; i++) {
+                    if (i < p.nb) {
+                        ar[i] += zr * w.x - zi * w.y;
+                        ai[i] += zr * w.y + zi * w.x;
+                        w = dmul(w, ws);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < MAXB; i++) { r.dsum[2 * i] = ar[i]; r.dsum[2 * i + 1] = ai[i]; }
+        } else if (tid == 0) {
+            double* o = p.part + ((i64)blk.y * p.nblk + blk.x) * (2 * MAXB);
+#pragma unroll
+            for (int i = 0; i < 2 * MAXB; i++) o[i] = r.dsum[i];
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
 // KDfFinal: reduce the per-row window maxima of the |fft(x^p)| spectrum to the carrier bin,
 // df = freq(s)/p with the reference's inclusive linspace axis (godual_ranging.m:15,73 -- the
 // "+0.25 Hz" grid quirk; claudio_aligned_code_lo_separate.m:103,129), then build the two-level

@@ -55,6 +55,7 @@ public:
     virtual int fine_frequency(const RunArgs& a) = 0;   // A10: d_df += dfleftover, derotation tables rebuilt
     virtual int correlate(const RunArgs& a) = 0;
     virtual int window_spectrum(const RunArgs& a, const EstimatorCfg& e, float* d_win) = 0;
+    virtual int window_spectrum_block2(const RunArgs& a, const EstimatorCfg& e, float* d_win) = 0;
     virtual int bank(const RunArgs& a, int sub_mean, BankRow* d_out) = 0;
     virtual int debug_fetch(int what, int lane, void* host_out, size_t bytes) = 0;
 };
@@ -250,7 +251,8 @@ public:
 
     // Carrier estimator on blocks of 2N samples (the 2-s blocks of claudio_aligned_code_lo_separate.m:120-129):
     // first radix-2 split fused into the column-pass loads, two N-point transforms, one arg-max over both.
-    int estimate_block2(const RunArgs& a, const EstimatorCfg& e) override
+    // two N-point transforms of the even/odd radix-2 halves of every 2N-sample block, row pass in MODE
+    template <int MODE> int block2_passes(const RunArgs& a, const EstimatorCfg& e, float* d_win)
     {
         const int lanes = a.nrec * a.nch;
         if (lanes > max_lanes) return -2;
@@ -263,15 +265,30 @@ public:
             t.d_df_in = d_df;
             df_final(t, nullptr);
         }
-        typedef KRow<RS, RPC, ROW_FWD_ARGMAX> KR;
+        typedef KRow<RS, RPC, MODE> KR;
         for (int par = 0; par < 2; par++) {
             if (e.power == 4) { if (par) col_raw<24>(a, 0, N * a.nch); else col_raw<14>(a, 0, N * a.nch); }
             else { if (par) col_raw<22>(a, 0, N * a.nch); else col_raw<12>(a, 0, N * a.nch); }
             RowParams r = estimator_row(a, e, 2, par, 2 * N);
             r.key_off = par * NROWBLK;
+            r.winmag = d_win;
             be->template launch<KR>(pgrid<KR>((i64)NROWBLK * lanes), r);
         }
+        return 0;
+    }
+    int estimate_block2(const RunArgs& a, const EstimatorCfg& e) override
+    {
+        const int rc = block2_passes<ROW_FWD_ARGMAX>(a, e, nullptr);
+        if (rc != 0) return rc;
         df_final(a, &e, 2 * NROWBLK);
+        return be->ok() ? 0 : -1;
+    }
+    // |fft(x^p)|^2 of every window bin of the 2N-point block spectrum -> d_win[lane][win_hi-win_lo+1]
+    // (search_df runs on the 2-s block: claudio_aligned_code_re_separate.m:28-29,150)
+    int window_spectrum_block2(const RunArgs& a, const EstimatorCfg& e, float* d_win) override
+    {
+        const int rc = block2_passes<ROW_FWD_WINMAG>(a, e, d_win);
+        if (rc != 0) return rc;
         return be->ok() ? 0 : -1;
     }
 

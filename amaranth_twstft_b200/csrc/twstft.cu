@@ -488,36 +488,34 @@ int twstft_doppler_bank(twstft_plan* p, const int16_t* iq, int iq_on_device, siz
     return run_bank(p, d_win, dfs, nbins, sub_mean, results);
 }
 
-int twstft_search_df(twstft_plan* p, const int16_t* iq, int iq_on_device, size_t total_instants, int64_t offset,
-                     double df_threshold, int64_t* kbon, double* df_found, int32_t* ncand)
+// Body of search_df (claudio_aligned_code_re_separate.m:26-46).  `sp` owns the x^p spectrum (its estimator window
+// on the ls-block axis), `cp` owns the code and runs the per-candidate correlation on the window at d_win.
+static int search_df_core(twstft_plan* sp, const short2* d_blk, int ls, twstft_plan* cp, const short2* d_win,
+                          double df_threshold, int64_t* kbon, double* df_found, int32_t* ncand)
 {
-    if (!p || !p->pipe || !iq || !kbon) return TWSTFT_E_ARG;
-    if (!p->have_code) return fail(p, TWSTFT_E_NOCODE, "no PRN code installed");
-    if (offset < 0 || (size_t)(offset + p->cfg.nsamples) > total_instants)
-        return fail(p, TWSTFT_E_ARG, "window outside the buffer");
-    p->be.use();
-    const short2* d_win = stage_window(p, iq, iq_on_device, offset);
-    if (!d_win) return fail(p, TWSTFT_E_NOMEM, "device allocation failed");
-    const EstimatorCfg& e = p->est;
+    const EstimatorCfg& e = ls == 2 ? sp->est2 : sp->est;
     const size_t wlen = (size_t)(e.win_hi - e.win_lo + 1);
-    float* d_mag = (float*)p->be.alloc(sizeof(float) * wlen * p->nch);
-    if (!p->be.ok()) return fail(p, TWSTFT_E_NOMEM, "device allocation failed");
+    sp->be.use();
+    float* d_mag = (float*)sp->be.alloc(sizeof(float) * wlen * sp->nch);
+    if (!sp->be.ok()) return fail(sp, TWSTFT_E_NOMEM, "device allocation failed");
     i64 zero = 0;
-    p->be.h2d(p->d_off, &zero, sizeof(i64));
+    sp->be.h2d(sp->d_off, &zero, sizeof(i64));
     RunArgs a{};
-    a.d_raw = d_win; a.nrec = 1; a.nch = p->nch; a.rec_stride = 0; a.d_rec_offset = p->d_off;
-    a.estimate = 1; a.variant = p->cfg.variant; a.ddof = p->cfg.ddof; a.fs = p->cfg.fs;
+    a.d_raw = d_blk; a.nrec = 1; a.nch = sp->nch; a.rec_stride = 0; a.d_rec_offset = sp->d_off;
+    a.estimate = 1; a.variant = sp->cfg.variant; a.ddof = sp->cfg.ddof; a.fs = sp->cfg.fs;
     int rc = TWSTFT_OK;
-    std::vector<float> mag(wlen * p->nch);
-    if (p->pipe->window_spectrum(a, e, d_mag) != 0) rc = fail(p, TWSTFT_E_CUDA, p->be.err_string());
+    std::vector<float> mag(wlen * sp->nch);
+    const int src = ls == 2 ? sp->pipe->window_spectrum_block2(a, e, d_mag) : sp->pipe->window_spectrum(a, e, d_mag);
+    if (src != 0) rc = fail(sp, TWSTFT_E_CUDA, sp->be.err_string());
     if (rc == TWSTFT_OK) {
-        p->be.d2h(mag.data(), d_mag, sizeof(float) * wlen * p->nch);
-        p->be.sync();
-        if (!p->be.ok()) rc = fail(p, TWSTFT_E_CUDA, p->be.err_string());
+        sp->be.d2h(mag.data(), d_mag, sizeof(float) * wlen * sp->nch);
+        sp->be.sync();
+        if (!sp->be.ok()) rc = fail(sp, TWSTFT_E_CUDA, sp->be.err_string());
     }
-    p->be.free(d_mag);
+    sp->be.free(d_mag);
     if (rc != TWSTFT_OK) return rc;
-    for (int c = 0; c < p->nch; c++) {
+    cp->be.use();
+    for (int c = 0; c < sp->nch; c++) {
         // ktmp=find(d2(k) > median(d2(k))*df_threshold)   re_separate.m:29
         std::vector<double> v(wlen);
         for (size_t i = 0; i < wlen; i++) v[i] = sqrt((double)mag[(size_t)c * wlen + i]);
@@ -534,16 +532,104 @@ int twstft_search_df(twstft_plan* p, const int16_t* iq, int iq_on_device, size_t
         if (cand.empty() || cand.size() >= 100) continue;          // re_separate.m:31
         std::vector<double> dfs(cand.size());
         for (size_t i = 0; i < cand.size(); i++) dfs[i] = axis_value(e, cand[i]) / (double)e.power;
-        std::vector<twstft_bank_result> rows(cand.size() * p->nch);
-        rc = run_bank(p, d_win, dfs.data(), dfs.size(), e.sub_mean, rows.data());
+        std::vector<twstft_bank_result> rows(cand.size() * cp->nch);
+        rc = run_bank(cp, d_win, dfs.data(), dfs.size(), e.sub_mean, rows.data());   // y=d(1:length(fcode)).*lo (:35)
         if (rc != TWSTFT_OK) return rc;
         for (size_t i = 0; i < cand.size(); i++)
-            if (rows[i * p->nch + c].metric > 100.0) {             // "SNR > 20 dB", last accepted wins (:42)
+            if (rows[i * cp->nch + c].metric > 100.0) {            // "SNR > 20 dB", last accepted wins (:42)
                 kbon[c] = cand[i] + 1;
                 if (df_found) df_found[c] = dfs[i];
             }
     }
     return TWSTFT_OK;
+}
+
+int twstft_search_df(twstft_plan* p, const int16_t* iq, int iq_on_device, size_t total_instants, int64_t offset,
+                     double df_threshold, int64_t* kbon, double* df_found, int32_t* ncand)
+{
+    if (!p || !p->pipe || !iq || !kbon) return TWSTFT_E_ARG;
+    if (!p->have_code) return fail(p, TWSTFT_E_NOCODE, "no PRN code installed");
+    if (offset < 0 || (size_t)(offset + p->cfg.nsamples) > total_instants)
+        return fail(p, TWSTFT_E_ARG, "window outside the buffer");
+    p->be.use();
+    const short2* d_win = stage_window(p, iq, iq_on_device, offset);
+    if (!d_win) return fail(p, TWSTFT_E_NOMEM, "device allocation failed");
+    return search_df_core(p, d_win, 1, p, d_win, df_threshold, kbon, df_found, ncand);
+}
+
+int twstft_search_df_block(twstft_plan* est, twstft_plan* cor, const int16_t* iq, int iq_on_device, int ls,
+                           double df_threshold, int64_t* kbon, double* df_found, int32_t* ncand)
+{
+    if (!est || !cor || !est->pipe || !cor->pipe || !iq || !kbon || (ls != 1 && ls != 2)) return TWSTFT_E_ARG;
+    if (!cor->have_code) return fail(cor, TWSTFT_E_NOCODE, "no PRN code installed");
+    if (est->nch != cor->nch || est->be.device != cor->be.device)
+        return fail(est, TWSTFT_E_ARG, "estimator and correlator plans must share the layout and the device");
+    if (cor->cfg.nsamples > est->cfg.nsamples * ls)
+        return fail(est, TWSTFT_E_ARG, "the correlation window is longer than the block");
+    if (ls == 2 && est->cfg.est_sub_mean)
+        return fail(est, TWSTFT_E_ARG, "ls=2 blocks are estimated on the raw samples (est_sub_mean=0)");
+    est->be.use();
+    const short2* d_blk = reinterpret_cast<const short2*>(iq);
+    if (!iq_on_device) {
+        if (ensure_raw(est) != 0) return fail(est, TWSTFT_E_NOMEM, "device allocation failed");
+        est->be.h2d(est->d_raw, iq, sizeof(short2) * est->raw_elems_per_rec * ls);
+        est->be.sync();                      // the correlator plan reads the same staging on its own stream
+        d_blk = est->d_raw;
+    }
+    const int rc = search_df_core(est, d_blk, ls, cor, d_blk, df_threshold, kbon, df_found, ncand);
+    if (rc != TWSTFT_OK && cor != est && cor->err.size() && est->err.empty()) est->err = cor->err;
+    return rc;
+}
+
+// |fft(x.^p)| at `nbins` adjacent positions of the fftshift'ed spectrum of a buffer of ANY length
+int twstft_estimate_bins(twstft_plan* p, const int16_t* iq, int iq_on_device, size_t ninstants, int64_t s_first,
+                         int nbins, double* mag)
+{
+    if (!p || !p->pipe || !iq || !mag || nbins < 1 || nbins > KBinsDFT::MAXB) return TWSTFT_E_ARG;
+    const i64 L = (i64)ninstants;
+    if (L < 1 || L >= ((i64)1 << 31) || s_first < 0 || s_first + nbins > L)
+        return fail(p, TWSTFT_E_ARG, "bins outside the spectrum");
+    p->be.use();
+    const short2* d = reinterpret_cast<const short2*>(iq);
+    short2* tmp = nullptr;
+    if (!iq_on_device) {
+        tmp = (short2*)p->be.alloc(sizeof(short2) * ninstants * p->nch);
+        if (!p->be.ok()) return fail(p, TWSTFT_E_NOMEM, "device allocation failed");
+        p->be.h2d(tmp, iq, sizeof(short2) * ninstants * p->nch);
+        d = tmp;
+    }
+    BinsParams b{};
+    b.src = d; b.ninst = L; b.nch = p->nch; b.power = p->est.power; b.nb = nbins;
+    b.k0 = (s_first + (L + 1) / 2) % L;      // fftshift: shifted[s] = X[(s + ceil(L/2)) mod L]
+    i64 nblk = (L + KBinsDFT::NT - 1) / KBinsDFT::NT;
+    const i64 wave = (i64)p->be.num_sms * 4;
+    if (nblk > wave) nblk = wave;
+    b.nblk = (int)nblk;
+    const size_t npart = (size_t)p->nch * nblk * 2 * KBinsDFT::MAXB;
+    b.part = (double*)p->be.alloc(sizeof(double) * npart);
+    int rc = TWSTFT_OK;
+    if (!p->be.ok()) rc = fail(p, TWSTFT_E_NOMEM, "device allocation failed");
+    if (rc == TWSTFT_OK) {
+        p->be.launch<KBinsDFT>(dim3((unsigned)nblk, p->nch, 1), b);
+        std::vector<double> part(npart);
+        p->be.d2h(part.data(), b.part, sizeof(double) * npart);
+        p->be.sync();
+        if (!p->be.ok()) rc = fail(p, TWSTFT_E_CUDA, p->be.err_string());
+        else
+            for (int c = 0; c < p->nch; c++)
+                for (int i = 0; i < nbins; i++) {
+                    double re = 0.0, im = 0.0;
+                    for (i64 k = 0; k < nblk; k++) {
+                        const double* o = &part[((size_t)c * nblk + k) * 2 * KBinsDFT::MAXB];
+                        re += o[2 * i];
+                        im += o[2 * i + 1];
+                    }
+                    mag[(size_t)c * nbins + i] = hypot(re, im);
+                }
+    }
+    p->be.free(b.part);
+    if (tmp) p->be.free(tmp);
+    return rc;
 }
 
 void* twstft_host_alloc(size_t bytes)

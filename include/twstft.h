@@ -19,6 +19,8 @@
  *   twstft_doppler_bank  per-bin body of search_df over a grid of offsets (cross-ambiguity)
  *                                                                                 claudio_aligned_code_re_separate.m:33-42
  *   twstft_search_df     k=search_df(d,k,df_threshold)                            claudio_aligned_code_re_separate.m:26-46
+ *   twstft_search_df_block  the same on the 2-s block the scripts hand it                 claudio_aligned_code_re_separate.m:150
+ *   twstft_estimate_bins d2=fftshift(abs(fft(d.^2))); max(d2(kbon-3:kbon+3)), d=[dold;block]  claudio_aligned_code_re_separate.m:166-168
  *   twstft_result        one row of the .mat variables                            godual_ranging.m:128-130, lo_separate.m:166
  *
  * Conventions: plain C, caller owns every host buffer, the plan owns device memory and streams,
@@ -144,6 +146,21 @@ int twstft_doppler_bank(twstft_plan* plan, const int16_t* iq, int iq_on_device, 
  * ncand[ch] = number of candidates.  (The reference runs it on 2-s blocks; here the block is the plan window.) */
 int twstft_search_df(twstft_plan* plan, const int16_t* iq, int iq_on_device, size_t total_instants, int64_t offset,
                      double df_threshold, int64_t* kbon, double* df_found, int32_t* ncand);
+
+/* search_df exactly as the re/ranging scripts call it (claudio_aligned_code_re_separate.m:26-46,150): the x^p
+ * spectrum is taken over the whole block of ls*est->nsamples sample instants (ls = 2, est->nsamples = fs: the 2-s
+ * block; window and freq axis of `est` on that block), every candidate is tested on the first cor->nsamples
+ * instants of the block against cor's code.  `est` and `cor` may be the same plan (ls = 1).  Outputs as above,
+ * kbon 1-based on the block axis. */
+int twstft_search_df_block(twstft_plan* est, twstft_plan* cor, const int16_t* iq, int iq_on_device, int ls,
+                           double df_threshold, int64_t* kbon, double* df_found, int32_t* ncand);
+
+/* d2=fftshift(abs(fft(d.^p))) evaluated at nbins (<= 8) adjacent 0-based positions s_first.. of the shifted axis,
+ * for a buffer of ANY length ninstants (the re/ranging scripts take it over d=[dold ; block] and look at
+ * kbon-3:kbon+3 only, claudio_aligned_code_re_separate.m:166-168): direct fp64 evaluation, one pass over the
+ * buffer.  mag[ch*nbins + i]. */
+int twstft_estimate_bins(twstft_plan* plan, const int16_t* iq, int iq_on_device, size_t ninstants, int64_t s_first,
+                         int nbins, double* mag);
 
 /* The same estimator on nblocks blocks of ls*N sample instants.  ls = 2 with N = fs is the 2-s block of
  * acquisition/claudio_aligned_code_lo_separate.m:120-129 (freq=linspace(-fs/2,fs/2-fs/fs,fs*ls), raw samples

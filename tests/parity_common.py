@@ -230,3 +230,67 @@ def run_ktrack(lib, fs=250000.0, n=10000, nblocks=2.3, delay=3000.0, df=1234.5, 
     assert np.max(np.abs(got["puissance1"] / ref["puissance1"] - 1)) < 1e-3
     assert abs(got["puissancenoise"] / ref["puissancenoise"] - 1) < 1e-3
     return got
+
+
+def run_ktrack_re(lib, fs=250000.0, n=10000, nblocks=2.3, delay=3000.4, df=50321.5, seed=11, max_batch=8, mode="re",
+                  skip_s=2.0, window_hz=None):
+    """The re/ranging production loop (claudio_aligned_code_re_separate.m:126-203) through KTracker against its
+    statement-by-statement oracle: kbon and df per block bit-exact (search_df on the block at `skip_s`, then the
+    seven-bin estimator on [dold ; block]), same MOVED windows, fractional indice1, every window within tolerance."""
+    from amaranth_twstft_b200.ktrack import KTracker, WINDOWS
+    from oracle import ktrack as okt
+    bits, code = make_code(n)
+    nsamp = int(nblocks * 2 * fs)
+    raw = synth.stream_single(code, nsamp, seed, delay=delay, df=df, fs=fs, dc=(30.0, -12.0))
+    win = window_hz or WINDOWS[(mode, 0)]
+    with KTracker(bits, fs=fs, ls=2, max_batch=max_batch, lib=lib, mode=mode, skip_s=skip_s, window_hz=win) as kt:
+        got = kt.process_file(raw)
+    ref = okt.re_separate(raw, code, fs=fs, ls=2, window_hz=win, skip_s=skip_s)
+    assert got is not None and ref is not None
+    assert not got["status"], got["status"]
+    assert got["kbon"] == ref["kbon"], (got["kbon"], ref["kbon"])
+    assert np.array_equal(got["df"], ref["df"]), (got["df"], ref["df"])
+    assert np.array_equal(got["moved"], ref["moved"]), (got["moved"], ref["moved"])
+    assert len(got["indice1"]) == len(ref["indice1"]) and len(ref["moved"]) >= 1
+    assert np.array_equal(got["indice1"], ref["indice1"]) and np.array_equal(got["movedval"], ref["movedval"])
+    assert np.max(np.abs(got["correction1"] - ref["correction1"])) / 3 < TOL_DELAY_SAMPLES
+    assert np.max(np.abs(np.angle(got["xval1"] * np.conj(ref["xval1"])))) < TOL_PHASE_RAD
+    snr = lambda o: 10 * np.log10(o["SNR1r"] + o["SNR1i"])
+    assert np.max(np.abs(snr(got) - snr(ref))) < TOL_SNR_DB
+    assert np.max(np.abs(got["puissance1"] / ref["puissance1"] - 1)) < 1e-3
+    return got
+
+
+def run_estimate_bins(lib, fs=250000.0, extra=1237, power=2, seed=5):
+    """d2=fftshift(abs(fft(d.^p))) at seven adjacent positions for a buffer whose length is NOT 2/5-smooth
+    (claudio_aligned_code_re_separate.m:166-167 takes it over [dold ; block]): against numpy's fp64 FFT to 1e-9, and
+    for an even and an odd length (fftshift differs)."""
+    bits, code = make_code(10000)
+    for add in (extra, extra + 1):
+        raw = synth.stream_single(code, int(2 * fs) + add, seed, delay=300.0, df=23456.5, fs=fs, dc=(30.0, -12.0))
+        d = oc.unpack_single(raw)
+        x = d ** power
+        d2 = np.fft.fftshift(np.abs(np.fft.fft(x)))
+        s0 = int(np.argmax(d2)) - 3
+        with Correlator(nsamples=int(fs), fs=fs, variant="K", layout="single", freq_axis="K", est_sub_mean=0,
+                        modulation="qpsk" if power == 4 else "bpsk", max_batch=1, lib=lib) as est:
+            mag = est.estimate_bins(raw, s0, 7)
+        assert int(np.argmax(mag[0])) == 3
+        assert np.max(np.abs(mag[0] / d2[s0:s0 + 7] - 1)) < 1e-9, mag[0] / d2[s0:s0 + 7] - 1
+
+
+def run_search_df_block(lib, fs=250000.0, n=10000, df=50321.5, seed=12, window=(92000.0, 108000.0)):
+    """search_df on the 2-s block the re/ranging scripts hand it (claudio_aligned_code_re_separate.m:26-46,150):
+    candidates from the 2*fs-point spectrum, each tested on the first N samples: kbon, df and candidate count exact."""
+    bits, code = make_code(n)
+    raw = synth.stream_single(code, int(2 * fs), seed, delay=1234.25, df=df, fs=fs, dc=(10.0, 5.0))
+    with Correlator(nsamples=int(fs), fs=fs, variant="K", layout="single", freq_axis="K", window_hz=window,
+                    est_sub_mean=0, max_batch=1, lib=lib) as est, \
+            Correlator(nsamples=n, fs=fs, variant="K", layout="single", max_batch=8, lib=lib) as cor:
+        cor.set_code(bits)
+        kbon, dff, ncand = est.search_df_block(cor, raw, ls=2, df_threshold=20.0)
+    freq = oc.freq_axis_K(fs, 2)
+    k = oc.window(freq, *window)
+    kref, tried = oc.search_df(oc.unpack_single(raw), k, 20.0, freq, oc.fcode_K(code), fs=fs)
+    assert ncand[0] == len(tried) and kref > 0, (ncand, tried)
+    assert kbon[0] == kref and dff[0] == freq[kref - 1] / 2, (kbon, kref, dff)

@@ -1,5 +1,6 @@
 """The C front end processing/C/godual.c (record loop of godual_ranging.m:57-130 over the C ABI) and its
 MAT-v5 writer.  On CPU it is linked against the test-only emulation library; on the GPU box against the product."""
+import json
 import os
 import subprocess
 
@@ -72,3 +73,74 @@ def test_godual_cli_emulation(tmp_path, remote):
 def test_godual_cli_cuda(tmp_path):
     exe = _build(os.path.dirname(pc.CUDA_LIB), "twstft", str(tmp_path / "godual"))
     _run_cli(exe, tmp_path, pc.CUDA_LIB, 0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# processing/C/claudio_aligned.c: the K-variant production loops (lo / re / ranging scripts) in C over the C ABI
+def _build_k(libdir, libname, out):
+    subprocess.check_call(["gcc", "-O2", "-std=c11", "-o", out, os.path.join(CDIR, "claudio_aligned.c"), f"-L{libdir}",
+                           f"-l{libname}", f"-Wl,-rpath,{libdir}", "-lm"])
+    return out
+
+
+def _run_k_cli(exe, tmp_path, lib, mode, fs=250000.0, n=N, nblocks=2.3, batch=8):
+    from amaranth_twstft_b200.ktrack import KTracker, PREFIX
+    bits, code = pc.make_code(n)
+    df = {"lo": 1234.5, "re": 50321.5, "ranging": -2222.25}[mode]
+    skip_s = 2.0
+    raw = synth.stream_single(code, int(nblocks * 2 * fs), 9, delay=0.3 * n + 0.4, df=df, fs=fs, dc=(30.0, -12.0))
+    data = tmp_path / "1716807811_1716808150.994543932_1.bin"
+    data.write_bytes(raw.tobytes())
+    codef = tmp_path / "n_code.bin"
+    codef.write_bytes(bits.tobytes())
+    out = subprocess.run([exe, mode, str(data), str(codef), "0", str(tmp_path), repr(fs), repr(skip_s), str(batch)],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    mat = scipy.io.loadmat(str(tmp_path / (PREFIX[mode] + "1716807811_1716808150.994543932_1.mat")))
+    with KTracker(bits, fs=fs, ls=2, max_batch=batch, lib=lib, mode=mode, skip_s=skip_s) as kt:
+        ref = kt.process_file(raw)
+    assert ref is not None and not ref["status"] and len(ref["moved"]) >= 1
+    # same library underneath: every stored number is identical, in the order/shape of the reference's own files
+    schema = json.load(open(os.path.join(pc.ROOT, "tests", "golden", "mat_schema.json")))
+    names = list(next(v for k, v in schema.items() if "localclaudio" in k))
+    assert [k for k in mat if not k.startswith("__")] == names
+    for name in ("correction1", "df", "indice1", "SNR1i", "SNR1r", "puissance1", "xval1", "moved", "movedval", "code"):
+        assert mat[name].shape == (1, len(ref[name])), (name, mat[name].shape)
+        assert np.array_equal(mat[name][0], ref[name]), name
+    assert mat["xval1"].dtype == np.complex128
+    assert mat["puissancecode"][0, 0] == ref["puissancecode"] and mat["puissancenoise"][0, 0] == ref["puissancenoise"]
+    lines = out.stdout.replace("\r", "").strip().splitlines()
+    assert lines[0].startswith("n\tdt1\tdf1\tP1\tSNR1")
+    rows = [ln.split("\t") for ln in lines[1:] if not ln.startswith("MOVED")]
+    assert len(rows) == len(ref["indice1"]) and sum(ln.startswith("MOVED") for ln in lines) == len(ref["moved"])
+    i = len(rows) - 1
+    assert abs(float(rows[i][1]) - (ref["indice1"][i] - 1 + ref["correction1"][i]) / fs / 3) < 1e-12
+    return ref
+
+
+@pytest.mark.skipif(not os.path.exists(pc.EMU_LIB), reason="emulation library not built")
+@pytest.mark.parametrize("mode", ["lo", "re", "ranging"])
+def test_claudio_aligned_cli_emulation(tmp_path, mode):
+    exe = _build_k(os.path.dirname(pc.EMU_LIB), "twstft_emu", str(tmp_path / "claudio_aligned_emu"))
+    _run_k_cli(exe, tmp_path, pc.EMU_LIB, mode)
+
+
+@pytest.mark.skipif(not os.path.exists(pc.EMU_LIB), reason="emulation library not built")
+def test_claudio_aligned_cli_reports_missing_carrier(tmp_path):
+    """re/ranging on noise: the script would loop for ever; the build exits with status 2."""
+    exe = _build_k(os.path.dirname(pc.EMU_LIB), "twstft_emu", str(tmp_path / "claudio_aligned_emu"))
+    rng = np.random.default_rng(5)
+    raw = rng.normal(0, 3000, int(2.2 * 2 * 250000) * 2).round().astype(np.int16)
+    (tmp_path / "noise_2.bin").write_bytes(raw.tobytes())
+    (tmp_path / "n_code.bin").write_bytes(pc.make_code(N)[0].tobytes())
+    out = subprocess.run([exe, "re", str(tmp_path / "noise_2.bin"), str(tmp_path / "n_code.bin"), "0", str(tmp_path),
+                          "250000", "0.5", "8"], capture_output=True, text=True)
+    assert out.returncode == 2 and "carrier not found" in out.stderr
+    assert not (tmp_path / "remoteclaudionoise_2.mat").exists()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["lo", "re"])
+def test_claudio_aligned_cli_cuda(tmp_path, mode):
+    exe = _build_k(os.path.dirname(pc.CUDA_LIB), "twstft", str(tmp_path / "claudio_aligned"))
+    _run_k_cli(exe, tmp_path, pc.CUDA_LIB, mode)

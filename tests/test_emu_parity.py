@@ -186,3 +186,34 @@ def test_k_result_file_has_the_reference_schema(tmp_path):
         assert str(m[name].dtype) == meta["dtype"], (name, m[name].dtype, meta["dtype"])
     assert m["indice1"].shape == m["correction1"].shape == m["xval1"].shape == m["SNR1r"].shape
     assert m["code"].shape == (1, 10000)
+
+
+def test_k_re_tracking_loop_search_and_fractional_index():
+    """claudio_aligned_code_re_separate.m: search_df on the block at skip_s, seven-bin estimator on [dold ; block],
+    un-floored indice1 -> fractional dindex and round() slices."""
+    got = pc.run_ktrack_re(pc.EMU_LIB)
+    assert len(got["df"]) == 2 and got["indice1"][1] != np.floor(got["indice1"][1])
+
+
+def test_k_ranging_tracking_loop():
+    pc.run_ktrack_re(pc.EMU_LIB, mode="ranging", df=1234.5, delay=777.7, skip_s=0.0)
+
+
+def test_k_re_returns_none_without_carrier():
+    from amaranth_twstft_b200.ktrack import KTracker
+    from oracle import ktrack as okt
+    bits, code = pc.make_code(10000)
+    raw = np.random.default_rng(3).normal(0, 3000, int(2.1 * 2 * 250000) * 2).round().astype(np.int16)
+    with KTracker(bits, fs=250000.0, ls=2, max_batch=8, lib=pc.EMU_LIB, mode="re", skip_s=0.5) as kt:
+        assert kt.process_file(raw) is None
+    assert okt.re_separate(raw, code, fs=250000.0, skip_s=0.5) is None
+
+
+def test_estimate_bins_any_length():
+    pc.run_estimate_bins(pc.EMU_LIB)
+    pc.run_estimate_bins(pc.EMU_LIB, power=4, extra=333)
+
+
+def test_search_df_on_two_second_block():
+    pc.run_search_df_block(pc.EMU_LIB)
+    pc.run_search_df_block(pc.EMU_LIB, df=-3456.25, window=(-8000.0, 8000.0))      # ranging window

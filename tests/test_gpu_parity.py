@@ -119,3 +119,26 @@ def test_k_tracking_loop_production_shape():
     got = pc.run_ktrack(pc.CUDA_LIB, fs=5e6, n=200000, nblocks=2.2, delay=61234.5, df=-3210.25, seed=20261017,
                         max_batch=32)
     assert len(got["df"]) == 2 and len(got["indice1"]) >= 98
+
+
+def test_k_re_tracking_loop_small():
+    pc.run_ktrack_re(pc.CUDA_LIB)
+
+
+def test_k_re_tracking_loop_production_shape():
+    """claudio_aligned_code_re_separate.m configuration: fs = 5 MS/s, 100 kchip/s code (N = 200 000), 2-s blocks,
+    remote window 92..108 kHz: search_df over the 10^7-point block spectrum, seven-bin estimator over
+    10^7 + len(dold) samples, 2.2 blocks with the code 61 234.5 samples late."""
+    got = pc.run_ktrack_re(pc.CUDA_LIB, fs=5e6, n=200000, nblocks=2.2, delay=61234.5, df=50321.5, seed=20261018,
+                           max_batch=32, skip_s=0.1)
+    assert len(got["df"]) == 2 and len(got["indice1"]) >= 98
+
+
+def test_estimate_bins_any_length():
+    pc.run_estimate_bins(pc.CUDA_LIB)
+    pc.run_estimate_bins(pc.CUDA_LIB, fs=5e6, extra=123457)
+
+
+def test_search_df_on_two_second_block():
+    pc.run_search_df_block(pc.CUDA_LIB)
+    pc.run_search_df_block(pc.CUDA_LIB, fs=5e6, n=200000)
