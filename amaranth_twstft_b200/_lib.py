@@ -22,7 +22,8 @@ EXPORTS = [
     "twstft_process_device", "twstft_process_windows", "twstft_estimate_carrier", "twstft_host_alloc",
     "twstft_host_free", "twstft_device_alloc", "twstft_device_free", "twstft_copy_to_device",
     "twstft_copy_to_host", "twstft_synchronize", "twstft_kernel_launches", "twstft_debug_fetch",
-    "twstft_window_bins", "twstft_doppler_bank", "twstft_search_df", "twstft_estimate_carrier_block", "twstft_timer_start", "twstft_timer_stop", "twstft_profile_enable", "twstft_profile_read",
+    "twstft_window_bins", "twstft_doppler_bank", "twstft_search_df", "twstft_estimate_carrier_block", "twstft_estimate_bins",
+    "twstft_search_df_block", "twstft_timer_start", "twstft_timer_stop", "twstft_profile_enable", "twstft_profile_read",
 ]
 
 
