@@ -25,7 +25,7 @@ template <> struct Bfly<4> {
     {
         const float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
         const float2 t2 = cadd(v[1], v[3]);
-        const float2 t3r = make_float2(v[1].y - v[3].y, v[3].x - v[1].x);   // -i*(v1 - v3)
+        const float2 t3r = rot_mi(csub(v[1], v[3]));                        // -i*(v1 - v3)
         v[0] = cadd(t0, t2);
         v[2] = csub(t0, t2);
         v[1] = cadd(t1, t3r);   // t1 - i*t3
@@ -39,12 +39,11 @@ template <> struct Bfly<5> {
         const float c1 = 0.30901699437494745f, c2 = -0.8090169943749473f;
         const float s1 = 0.9510565162951535f, s2 = 0.5877852522924732f;
         const float2 t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]);
-        const float2 t3r = make_float2(v[1].y - v[4].y, v[4].x - v[1].x);   // -i*(v1 - v4)
-        const float2 t4r = make_float2(v[2].y - v[3].y, v[3].x - v[2].x);   // -i*(v2 - v3)
+        const float2 t3 = csub(v[1], v[4]), t4 = csub(v[2], v[3]);
         const float2 a1 = caxpy(c2, t2, caxpy(c1, t1, v[0]));
         const float2 a2 = caxpy(c1, t2, caxpy(c2, t1, v[0]));
-        const float2 b1 = caxpy(s2, t4r, cscale(s1, t3r));      // -i*(s1*t3 + s2*t4)
-        const float2 b2 = caxpy(-s1, t4r, cscale(s2, t3r));     // -i*(s2*t3 - s1*t4)
+        const float2 b1 = rot_mi(caxpy(s2, t4, cscale(s1, t3)));    // -i*(s1*t3 + s2*t4)
+        const float2 b2 = rot_mi(caxpy(-s1, t4, cscale(s2, t3)));   // -i*(s2*t3 - s1*t4)
         v[0] = cadd(v[0], cadd(t1, t2));
         v[1] = cadd(a1, b1);
         v[4] = csub(a1, b1);
@@ -63,8 +62,7 @@ template <int R> HD float2 mul_root(float2 a, int t)
     if ((R % 4 == 0) && t == 3 * R / 4) return make_float2(-a.y, a.x);   // * (+i)
     float c, s;
     UnitRoots<R>::get(t, c, s);
-    const float2 m = cscale(c, a);                                       // a * (c - i s)
-    return make_float2(m.x + a.y * s, m.y - a.x * s);
+    return cmul_const(a, c, s);                                          // a * (c - i s)
 }
 
 // R = RA*RB: n = na*RB + nb, k = ka + RA*kb

@@ -72,12 +72,14 @@ HD float2 caxpy(float s, float2 a, float2 b)
     return make_float2(s * a.x + b.x, s * a.y + b.y);
 #endif
 }
-// a*b: one packed multiply by the broadcast real part, two scalar FMAs for the imaginary part
+// a*b in TWO packed instructions: t = b*(ax,ax); r = swap(b)*(-ay,ay) + t.  ptxas folds the half swap and
+// the single-half negation into operand modifiers of FFMA2 (SASS `-R.F32x2.LO_HI.NP, R.F32`), so no scalar
+// FFMA and no register moves remain (checked with cuobjdump; the scalar form cost three issue slots).
 HD float2 cmul(float2 a, float2 b)
 {
 #ifdef __CUDA_ARCH__
-    const float2 t = upk(mul2(pk(a.x, a.x), pk(b)));
-    return make_float2(fmaf(-a.y, b.y, t.x), fmaf(a.y, b.x, t.y));
+    const u64 t = mul2(pk(a.x, a.x), pk(b));
+    return upk(fma2(pk(b.y, b.x), pk(-a.y, a.y), t));
 #else
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 #endif
@@ -86,12 +88,24 @@ HD float2 cmul(float2 a, float2 b)
 HD float2 cmulc(float2 a, float2 b)
 {
 #ifdef __CUDA_ARCH__
-    const float2 t = upk(mul2(pk(b.x, b.x), pk(a)));
-    return make_float2(fmaf(a.y, b.y, t.x), fmaf(-a.x, b.y, t.y));
+    const u64 t = mul2(pk(b.x, b.x), pk(a));
+    return upk(fma2(pk(a.y, a.x), pk(b.y, -b.y), t));
 #else
     return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
 #endif
 }
+// a*(c - i s), c and s compile-time constants of an in-register butterfly
+HD float2 cmul_const(float2 a, float c, float s)
+{
+#ifdef __CUDA_ARCH__
+    return upk(fma2(pk(a.y, a.x), pk(s, -s), mul2(pk(c, c), pk(a))));
+#else
+    return make_float2(c * a.x + a.y * s, c * a.y - a.x * s);
+#endif
+}
+// -i*a and +i*a: register renames plus one sign, folded by ptxas into the consuming packed instruction
+HD float2 rot_mi(float2 a) { return make_float2(a.y, -a.x); }
+HD float2 rot_pi(float2 a) { return make_float2(-a.y, a.x); }
 HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 HD float2 cswap(float2 a) { return make_float2(a.y, a.x); }
 HD float cnorm(float2 a) { return a.x * a.x + a.y * a.y; }

@@ -67,7 +67,7 @@ struct KMean {
                 const int4* s4 = reinterpret_cast<const int4*>(s);
                 const i64 nquad = p.nelem >> 2;
                 int q0x = 0, q0y = 0, q1x = 0, q1y = 0;
-#pragma unroll 4
+#pragma unroll 8
                 for (i64 e = e0; e < nquad; e += stride) {
                     const int4 v = s4[e];
                     q0x += (int)(short)(v.x & 0xffff) + (int)(short)(v.z & 0xffff);

@@ -179,7 +179,9 @@ public:
         m.src = a.d_raw; m.nelem = N * a.nch; m.nch = a.nch; m.rec_stride = a.rec_stride;
         m.rec_offset = a.d_rec_offset; m.sums = d_sums;
         i64 per = (m.nelem + KMean::NT - 1) / KMean::NT;
-        int nblk = (int)(per < 592 ? (per < 1 ? 1 : per) : 592);
+        // two resident waves (148 SMs x 4 CTAs) over the whole batch: CTAs live long enough to hide their launch
+        const i64 cap = (2 * 592 + a.nrec - 1) / a.nrec;
+        int nblk = (int)(per < cap ? (per < 1 ? 1 : per) : cap);
         m.nblk = nblk;
         be->template launch<KMean>(dim3(nblk, a.nrec, 1), m);
     }
