@@ -32,7 +32,7 @@ class Config(C.Structure):
         ("fs", C.c_double), ("nsamples", C.c_int64), ("samples_per_chip", C.c_int), ("variant", C.c_int),
         ("modulation", C.c_int), ("nint", C.c_int), ("layout", C.c_int), ("freq_axis", C.c_int),
         ("win_lo_hz", C.c_double), ("win_hi_hz", C.c_double), ("est_sub_mean", C.c_int), ("ddof", C.c_int),
-        ("max_batch", C.c_int), ("device_id", C.c_int), ("fine_freq", C.c_int),
+        ("max_batch", C.c_int), ("device_id", C.c_int), ("fine_freq", C.c_int), ("code_window", C.c_int),
     ]
 
 

@@ -350,6 +350,7 @@ struct PeakEvalParams {
     int L1, N2;
     i64* p0_out;           // [lane]
     double* part;          // [lane][NPTS][2]
+    const i64* p0_in;      // optional [lane]: evaluate around this index instead of the tiles' maximum
 };
 // One CTA per (lag, lane): prnmap[p] = sum_k1 B[q][k1][n2] exp(+2 pi i k1 n1 / L1) with
 // p = nq*(n1*N2 + n2) + q, i.e. one output of the inverse column transform evaluated directly
@@ -376,7 +377,7 @@ template <int NPTS, int DLO> struct KPeakEvalT {
             r.dsum[0] = r.dsum[1] = 0.0;
         } else if (PH == 1) {
             const i64 M = (i64)p.nq * p.N;
-            const i64 p0 = (i64)key_index(r.key);
+            const i64 p0 = p.p0_in ? p.p0_in[lane] : (i64)key_index(r.key);
             i64 pp = (p0 + DLO + d) % M;
             if (pp < 0) pp += M;
             const int q = (int)(pp % p.nq);
@@ -395,7 +396,7 @@ template <int NPTS, int DLO> struct KPeakEvalT {
         } else if (tid == 0) {
             p.part[(lane * NPTS + d) * 2] = r.dsum[0];
             p.part[(lane * NPTS + d) * 2 + 1] = r.dsum[1];
-            if (d == 0) p.p0_out[lane] = (i64)key_index(r.key);
+            if (d == 0 && !p.p0_in) p.p0_out[lane] = (i64)key_index(r.key);
         }
     }
 };
@@ -430,6 +431,10 @@ struct PeakFinParams {
     int ddof;                  // 1 = Octave var, 0 = numpy var
     double code_pow;           // mean |code|^2 (sum|yincode|^2 = code_pow * sum|yint|^2)
     Result* out;               // [lane]
+    i64* pc_out;               // optional [lane]: the decided 0-based peak index
+    int snr_only;              // 1: the lags are those of the UNWINDOWED correlation around the already decided
+                               //    peak p0 (C++ flavour, processing/CPP/main.cpp:319-357): only the SNR / power
+                               //    fields of `out` are rewritten
 };
 struct KPeakFinal {
     typedef PeakFinParams Params;
@@ -468,7 +473,7 @@ struct KPeakFinal {
         const int c0 = -PEAK_DLO;
         int c = c0;
         i64 pc = p0;
-        for (int t = -1; t <= 1; t += 2) {
+        for (int t = -1; t <= 1 && !p.snr_only; t += 2) {
             i64 pt = (p0 + t) % M;
             if (pt < 0) pt += M;
             const int ct = c0 + t;
@@ -482,11 +487,16 @@ struct KPeakFinal {
         if (p.variant == 0 && (pc == 0 || pc == M - 1)) status += 1.0;   // Octave would index out of range
         const double ap1 = sqrt(a2[cp]);
         Result o;
+        if (p.snr_only) o = p.out[lane];
+        if (p.pc_out) p.pc_out[lane] = pc;
+        if (!p.snr_only) {
         o.indice = (double)(pc + 1);
         o.correction = (am1 - ap1) / (am1 + ap1 - 2.0 * a0) / 2.0;
         o.xval_re = sr[c]; o.xval_im = si[c];
         o.xvalm1_re = sr[c - 1]; o.xvalm1_im = si[c - 1];
         o.xvalp1_re = sr[cp]; o.xvalp1_im = si[cp];
+        o.status = status;
+        }
         // "Claudio" SNR through the spectral identity: the mean of yincode is the sum of
         // three adjacent correlation lags / M; sum|yint|^2 follows from Parseval.
         double mr, mi;
@@ -506,12 +516,42 @@ struct KPeakFinal {
         o.SNRr = mr * mr / var_c;
         o.SNRi = mi * mi / var_c;
         o.df = p.df[lane];
-        o.puissance = (E / n - y0n / n) / (n - (double)p.ddof);
+        o.puissance = p.snr_only ? E : (E / n - y0n / n) / (n - (double)p.ddof);   // C++: sum |Y|^2 (main.cpp:295)
         o.puissancecode = mr * mr + mi * mi;
         o.puissancenoise = var_c;
         o.carrier_bin = (double)p.sbin[lane];
-        o.status = status;
         p.out[lane] = o;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// KCodeWindow: the C++ program multiplies the conjugated code spectrum by hamming(N) over the BIN index
+// (processing/CPP/main.cpp:717-719; SigPack: 0.54 - 0.46 cos(2 pi k/(N-1))).  Position (k1,k2) of the transposed
+// spectrum holds bin k = k1 + N1*k2.
+struct CodeWinParams {
+    const float2* src;
+    float2* dst;
+    i64 N;
+    int N1, L;
+};
+struct KCodeWindow {
+    typedef CodeWinParams Params;
+    static const char* name() { return "code_window"; }
+    static constexpr bool PERSISTENT = false;
+    static constexpr int NT = 256, MINB = 4, NPH = 1, NSUM = 1;
+    struct Regs { u64 key; double dsum[NSUM]; };
+    static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }
+    static HD constexpr int sync_after(int) { return SYNC_BARRIER; }
+    template <int PH> static HD void phase(const Params& p, const Blk& blk, int tid, Regs&, unsigned char*)
+    {
+        const i64 e = (i64)blk.x * NT + tid;
+        if (e >= p.N) return;
+        const i64 k1 = e / p.L, k2 = e % p.L;
+        const i64 k = k1 + (i64)p.N1 * k2;
+        const double2 c = cis_cycles_d((double)k / (double)(p.N - 1));
+        const float w = (float)(0.54 - 0.46 * c.x);
+        const float2 x = p.src[e];
+        p.dst[e] = make_float2(x.x * w, x.y * w);
     }
 };
 

@@ -50,6 +50,7 @@ public:
     virtual size_t bytes_per_lane() const = 0;
     virtual int setup(Backend* be, int max_lanes, int nq) = 0;
     virtual int build_code(const unsigned char* d_bits, int rep, int qpsk, float2 mean, double code_pow) = 0;
+    virtual void set_code_window(int w) = 0;   // 1: Hamming-windowed code spectrum (C++ program); before build_code
     virtual int estimate(const RunArgs& a, const EstimatorCfg& e) = 0;   // -> d_df/d_sbin (+ derotation tables)
     virtual int estimate_block2(const RunArgs& a, const EstimatorCfg& e) = 0;
     virtual int fine_frequency(const RunArgs& a) = 0;   // A10: d_df += dfleftover, derotation tables rebuilt
@@ -86,7 +87,8 @@ public:
     {
         if (!be) return;
         void* all[] = {d_blob_c, d_blob_r, d_code, d_qconst, d_A, d_B, d_sums, d_energy, d_df, d_peakpart,
-                       d_keyrow, d_keycol, d_sbin, d_p0, d_y0, d_lrow, d_lcol, d_stat, d_bankpart, d_ang, d_finepart};
+                       d_keyrow, d_keycol, d_sbin, d_p0, d_y0, d_lrow, d_lcol, d_stat, d_bankpart, d_ang, d_finepart,
+                       d_code_win};
         for (void* p : all) be->free(p);
     }
     i64 size() const override { return N; }
@@ -154,6 +156,9 @@ public:
         return be->ok() ? 0 : -1;
     }
 
+    int code_window = 0;       // 1: correlate against hamming(N) .* conj(fft(code)) (processing/CPP/main.cpp:717-719)
+    float2* d_code_win = nullptr;
+    void set_code_window(int w) override { code_window = w; }
     double code_pow = 1.0;     // mean |code|^2: 1 for the +/-1 BPSK replica, ~0.5 for the QPSK one
     int build_code(const unsigned char* d_bits, int rep, int qpsk, float2 mean, double cpow) override
     {
@@ -168,6 +173,12 @@ public:
         r.nlanes = 1;
         typedef KRow<RS, RPC, ROW_FWD_STORE> KR;
         be->template launch<KR>(pgrid<KR>(NROWBLK), r);
+        if (code_window) {
+            if (!d_code_win) d_code_win = dalloc<float2>(N);
+            CodeWinParams w{};
+            w.src = d_code; w.dst = d_code_win; w.N = N; w.N1 = L1; w.L = N2;
+            be->template launch<KCodeWindow>(dim3((unsigned)((N + KCodeWindow::NT - 1) / KCodeWindow::NT), 1, 1), w);
+        }
         return be->ok() ? 0 : -1;
     }
 
@@ -399,7 +410,8 @@ public:
         r.src = d_A; r.dst = d_B; r.blob = d_blob_r; r.code = d_code; r.qconst = d_qconst; r.N = N; r.N1 = L1;
         r.invN = 1.0 / (double)N; r.invM = 1.0 / ((double)nq * (double)N); r.nlanes = lanes; r.nblk = NROWBLK;
         r.conj_mode = a.variant; r.part_energy = d_energy; r.y0 = d_y0;
-        {
+        if (code_window && d_code_win) r.code = d_code_win;
+        auto row_corr = [&]() {
             i64 g = (i64)NROWBLK * lanes;
             typedef KRowCorr<RS, RPC, 3> K3;
             typedef KRowCorr<RS, RPC, 1> K1;
@@ -407,7 +419,8 @@ public:
             if (g > wave) g = wave;
             if (nq == 3) be->template launch<K3>(dim3((unsigned)g, 1, 1), r);
             else be->template launch<K1>(dim3((unsigned)g, 1, 1), r);
-        }
+        };
+        row_corr();
         ColParams c{};
         c.src = d_B; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.invN = 1.0 / (double)N; c.nch = 1; c.nq = nq; c.part_key = d_keycol;
         c.ntx = NCOLTILE_I; c.ny = lanes * nq;
@@ -421,7 +434,18 @@ public:
         pf.part = d_peakpart; pf.nblk = 1; pf.part_energy = d_energy; pf.nen = NROWBLK; pf.y0 = d_y0;
         pf.code_pow = code_pow; pf.p0 = d_p0; pf.df = d_df; pf.sbin = d_sbin; pf.N = N; pf.nq = nq; pf.variant = a.variant; pf.ddof = a.ddof;
         pf.out = a.d_out;
+        pf.pc_out = (code_window && d_code_win) ? d_p0 : nullptr;
         be->template launch<KPeakFinal>(dim3(1, lanes, 1), pf);
+        if (code_window && d_code_win) {
+            // C++ flavour: the SNR despreads yint with the PLAIN code (main.cpp:319-357), i.e. it needs the lags of the
+            // unwindowed correlation around the peak just decided: second row pass against d_code, no column pass
+            r.code = d_code;
+            row_corr();
+            pe.p0_in = d_p0;
+            be->template launch<KPeakEval>(dim3(PEAK_NPTS, lanes, 1), pe);
+            pf.snr_only = 1; pf.pc_out = nullptr;
+            be->template launch<KPeakFinal>(dim3(1, lanes, 1), pf);
+        }
         return be->ok() ? 0 : -1;
     }
 

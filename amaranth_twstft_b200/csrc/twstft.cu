@@ -82,6 +82,7 @@ void twstft_default_config(twstft_config* c)
     c->max_batch = 4;
     c->device_id = 0;
     c->fine_freq = 0;
+    c->code_window = TWSTFT_CODEWIN_NONE;
 }
 
 int twstft_plan_create(const twstft_config* cfg, twstft_plan** out)
@@ -93,6 +94,8 @@ int twstft_plan_create(const twstft_config* cfg, twstft_plan** out)
     *out = p;   // returned even on failure so that twstft_last_error can be read; destroy it either way
     if (cfg->nsamples <= 0 || cfg->max_batch <= 0 || cfg->fs <= 0 || cfg->samples_per_chip <= 0)
         return fail(p, TWSTFT_E_ARG, "bad configuration");
+    if (cfg->code_window != TWSTFT_CODEWIN_NONE && cfg->code_window != TWSTFT_CODEWIN_HAMMING)
+        return fail(p, TWSTFT_E_ARG, "unknown code_window");
     if (cfg->nint != 0 && cfg->nint != 1)
         return fail(p, TWSTFT_E_ARG, "only Nint=1 (x3) and Nint=0 are supported (the reference uses Nint=1)");
     if (p->be.init(cfg->device_id) != 0)
@@ -180,6 +183,7 @@ static int install_code(twstft_plan* p, const unsigned char* host_bits, size_t n
         // mean |codec|^2 with bits in {0,1}: E[(a-ma)^2] + E[(b-mb)^2] = ma(1-ma) + mb(1-mb)
         code_pow = ma * (1.0 - ma) + mb * (1.0 - mb);
     }
+    p->pipe->set_code_window(p->cfg.code_window == TWSTFT_CODEWIN_HAMMING);
     if (p->pipe->build_code(p->d_bits, p->cfg.samples_per_chip, qpsk, mean, code_pow) != 0)
         return fail(p, TWSTFT_E_CUDA, p->be.err_string());
     p->be.sync();

@@ -121,6 +121,27 @@ class ClockSampler:
                 "how": "NVML, 1 ms period, sampled only inside the timed region"}
 
 
+def bind_to_gpu_numa(index):
+    """Pin this process to the CPUs NVML reports as local to GPU `index`, before the pinned staging buffers are
+    allocated: with one rank per GPU every rank then streams its 40 MB/record from its own socket's memory."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        words = (os.cpu_count() + 63) // 64
+        mask = nv.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"bound to {len(cpus)} GPU-local cpus"
+    except Exception as e:      # affinity is an optimisation only
+        return f"unbound ({type(e).__name__})"
+    return "unbound"
+
+
 def oracle_record(raw, code):
     from oracle import correlator as oc
     freq = oc.freq_axis_G(FS, N)
@@ -211,6 +232,7 @@ def main():
 
     from amaranth_twstft_b200.api import Correlator
     R = args.records_per_step
+    numa = bind_to_gpu_numa(local)
     cor = Correlator(nsamples=N, fs=FS, max_batch=R, device=local)
     assert cor.backend == "cuda"
     bits = cor.gen_code(CODE[0], CODE[1])
@@ -296,7 +318,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: two-channel 1-s 5 MS/s BPSK records, 22-bit taps-3 code, x3 interpolation",
                        "records_per_step": R, "samples_per_record": N, "l2": f"inputs larger than L2: {R} distinct "
-                       f"records = {R * rec_bytes / 1e6:.0f} MB raw, {R * 2 * 200:.0f} MB intermediates per step"},
+                       f"records = {R * rec_bytes / 1e6:.0f} MB raw, {R * 2 * 200:.0f} MB intermediates per step", "host_numa": numa},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": R * rec_bytes,
                     "d2h_bytes_per_step": int(res_e2e.nbytes)},

@@ -51,6 +51,9 @@ extern "C" {
 #define TWSTFT_AXIS_G 0 /* freq=linspace(-fs/2,fs/2,n)      godual_ranging.m:73   */
 #define TWSTFT_AXIS_K 1 /* freq=linspace(-fs/2,fs/2-1,n)    lo_separate.m:103     */
 
+#define TWSTFT_CODEWIN_NONE 0    /* fcode = conj(fft(code))                      godual_ranging.m:66          */
+#define TWSTFT_CODEWIN_HAMMING 1 /* fcode = conj(fft(code)) .* hamming(N) over bins processing/CPP/main.cpp:717-719 */
+
 #define TWSTFT_OK 0
 #define TWSTFT_E_ARG (-1)
 #define TWSTFT_E_NODEVICE (-2)
@@ -80,6 +83,12 @@ typedef struct twstft_config {
                            100-tap smoothed angle(y(1:10:fs/3)), df += slope/2pi --
                            experiments/221219_twoway/processing/godual_ranging.py:26-30 (commented out at
                            processing/Octave/godual_ranging.m:19-24); 0 (default): off */
+    int code_window;    /* TWSTFT_CODEWIN_*: the C++ program correlates against a Hamming-windowed code spectrum but
+                           despreads the SNR estimate with the plain code (processing/CPP/main.cpp:319-357,717-719);
+                           with HAMMING the SNR/power fields therefore come from a second, unwindowed row pass around
+                           the peak decided on the windowed correlation, and `puissance` is sum|fft(y)|^2
+                           (main.cpp:295) instead of var(y).  Scales stay Octave's (ifft 1/n): FFTW's unnormalised
+                           values are 3N times xval*, and the stored correction1 is indice-1+correction */
 } twstft_config;
 
 /* One row of the reference's result variables, per channel and record (all doubles). */

@@ -141,6 +141,89 @@ def processing_G(d, k, freq, fcode, code, fs=FS, power=2, fine_freq=False, ddof=
     return out
 
 
+# --------------------------------------------------------------------------- C++ program (processing/CPP/main.cpp)
+def hamming_sigpack(n):
+    """SigPack 1.2.7 hamming(N) (processing/CPP/main.cpp:16,717): 0.54-0.46*cos(2*pi*i/(N-1)).  Third-party code,
+    not under /root/reference: parity with SigPack itself is UNPINNED."""
+    i = np.arange(int(n), dtype=np.float64)
+    return 0.54 - 0.46 * np.cos(2.0 * np.pi * i / (n - 1.0))
+
+
+def fcode_CPP(code):
+    """GoRanging::fill_fcode, main.cpp:658-725: conj(fft(code)) times hamming over the BIN index (:717-719)."""
+    return np.conj(_fft.fft(code)) * hamming_sigpack(len(code))
+
+
+def processing_CPP(d, df, fcode_win, code, fs=FS):
+    """GoRanging::_process_method, main.cpp:224-361, for one channel of one record.  `d` raw complex samples (the
+    mean is removed here, :248), `df` the file-wide offset (_foffset1/2, :270-275).  FFTW's backward transform is
+    unnormalised, so prnmap/yint are 3N times Octave's; indices are 0-based; var divides by n (:350).
+    Returns the values the C++ pushes into its vectors (:309-357)."""
+    n = len(d)
+    m3 = 3 * n
+    d = d - np.mean(d)
+    y = d * np.exp(-1j * 2 * np.pi * df * (np.arange(n) / fs))
+    ffty = _fft.fft(y)
+    puissance = float(np.sum(np.abs(ffty) ** 2))                       # :295
+    prnmap = _fft.ifft(_pad3(ffty * fcode_win)) * m3                    # :289-301, unnormalised
+    p0 = int(np.argmax(np.abs(prnmap)))                                 # :305
+    xval, xvalm1, xvalp1 = prnmap[p0], prnmap[(p0 - 1) % m3], prnmap[(p0 + 1) % m3]
+    a0, am1, ap1 = abs(xval), abs(xvalm1), abs(xvalp1)
+    corr = (am1 - ap1) / 2.0 / (am1 + ap1 - 2.0 * a0)                   # :309
+    yint = _fft.ifft(_pad3(ffty)) * m3                                  # :319-327
+    yincode = np.roll(yint, -(p0 - 1)) * np.repeat(code, 3)             # std::rotate by indice1-1, :332-338
+    snr1 = np.mean(yincode)
+    s = float(np.mean(np.abs(yincode - snr1) ** 2))                     # :342-350 (divides by n)
+    snr_r, snr_i = snr1.real ** 2 / s, snr1.imag ** 2 / s
+    return dict(p0=p0, correction=float(p0 + corr), xval=complex(xval), xvalm1=complex(xvalm1),
+                xvalp1=complex(xvalp1), df=float(df), puissance=puissance,
+                puissancecode=float(10 * np.log10(abs(snr1) ** 2)), SNR=float(10 * np.log10(snr_r + snr_i)))
+
+
+def df_CPP(raw_file, nch_total, fs=FS, dec=25, foffset=0.0, remote=0):
+    """GoRanging::df, main.cpp:363-450: one sample instant out of `dec` over the WHOLE file (no filter), derotated
+    by `foffset`, mean removed, squared, one FFT per channel; channel 1 looks at |f| < 16 kHz of the +-fs/2/dec
+    axis (kmin..kmax-1), channel 2 at every bin; df = freq[pos]/2 + foffset.  raw_file: int16 [I1 Q1 I2 Q2]..."""
+    r = np.asarray(raw_file, dtype=np.float64)
+    ninst = len(r) // 4
+    L = (len(r) * 2) // (2 * 4 * dec)                                   # ftell / (sizeof(int16)*4*N), :377
+    idx = np.arange(L) * dec
+    idx = idx[idx < ninst]
+    t = np.arange(len(idx)) * (dec / fs)
+    lo = np.exp(-1j * 2 * np.pi * foffset * t)
+    x1 = (r[4 * idx] + 1j * r[4 * idx + 1]) * lo
+    L = len(x1)
+    freq = np.linspace(-fs / 2 / dec, fs / 2 / dec, L)
+    frange = 8000.0
+    kmin, kmax = 0, 0
+    for i in range(L) if L < 4096 else ():                              # literal loop of :393-398 for small L
+        if freq[i] < 2 * frange:
+            kmax = i
+        if freq[i] <= -2 * frange:
+            kmin = i
+    if L >= 4096:
+        w = np.nonzero(freq < 2 * frange)[0]
+        kmax = int(w[-1]) if len(w) else 0
+        w = np.nonzero(freq <= -2 * frange)[0]
+        kmin = int(w[-1]) if len(w) else 0
+    x1 = x1 - np.mean(x1)
+    out = np.fft.fftshift(np.abs(_fft.fft(x1 * x1))) if L % 2 == 0 else None
+    if out is None:                                                     # memcpy halves of :413-414 for odd L
+        f = np.abs(_fft.fft(x1 * x1))
+        h = L // 2
+        out = np.concatenate([f[h:h + h], f[:h], f[2 * h:]])
+    pos1 = int(np.argmax(out[kmin:kmax])) + kmin
+    res = {1: freq[pos1] / 2.0 + foffset}
+    if remote == 0:
+        x2 = (r[4 * idx + 2] + 1j * r[4 * idx + 3]) * lo
+        x2 = x2 - np.mean(x2)
+        f = np.abs(_fft.fft(x2 * x2))
+        h = L // 2
+        out2 = np.concatenate([f[h:h + h], f[:h], f[2 * h:]])
+        res[2] = freq[int(np.argmax(out2))] / 2.0 + foffset
+    return res
+
+
 # --------------------------------------------------------------------------- variant K (A5-A9)
 def processing_K(d, df, fcode, code, fs=FS, ddof=1):
     """[xval,indice,correction,SNRr,SNRi,puissance,puissancecode,puissancenoise]=processing(d,k,df)

@@ -147,6 +147,46 @@ def run_variant_k(lib, n, delay, df=1234.5, seed=77):
     assert_row_matches(res[0, 0], ref, where=f"K N={n} delay={delay}")
 
 
+def cpp_rows(res, n):
+    """Library rows (code_window=1) -> the vectors the C++ program stores (processing/CPP/main.cpp:309-357):
+    FFTW's backward transform is unnormalised (x 3N), indices are 0-based, powers in dB."""
+    m3 = 3.0 * n
+    tot = res["SNRr"] + res["SNRi"]
+    return dict(correction=res["indice"] - 1.0 + res["correction"],
+                xval=(res["xval_re"] + 1j * res["xval_im"]) * m3,
+                xvalm1=(res["xvalm1_re"] + 1j * res["xvalm1_im"]) * m3,
+                xvalp1=(res["xvalp1_re"] + 1j * res["xvalp1_im"]) * m3,
+                SNR=10 * np.log10(tot), puissance=res["puissance"],
+                puissancecode=10 * np.log10(res["puissancecode"] * m3 * m3))
+
+
+def run_variant_cpp(lib, n, seeds=(5,), dfs=(4321.25, 0.0), max_batch=2):
+    """GoRanging::_process_method (processing/CPP/main.cpp:224-361): Hamming-windowed code spectrum, file-wide
+    df per channel, var / n, despreading with the plain code."""
+    bits, code = make_code(n)
+    recs = [synth.record_pair(code, s, ch1=dict(df=dfs[0] + 0.37), ch2=dict(df=dfs[1]))[0] for s in seeds]
+    with Correlator(nsamples=n, ddof=0, code_window=True, max_batch=max_batch, lib=lib) as cor:
+        cor.set_code(bits)
+        res = cor.process_windows(np.concatenate(recs), [i * n for i in range(len(recs))],
+                                  [list(dfs)] * len(recs))
+    fw = oc.fcode_CPP(code)
+    for i, raw in enumerate(recs):
+        d = oc.unpack_interleaved2(raw)
+        for ch in (0, 1):
+            o = oc.processing_CPP(d[ch], dfs[ch], fw, code)
+            r = cpp_rows(res[i, ch], n)
+            w = f"C++ N={n} seed={seeds[i]} ch{ch + 1}"
+            assert int(res[i, ch]["indice"]) - 1 == o["p0"], f"{w}: peak index"
+            assert abs(r["correction"] - o["correction"]) / 3.0 < TOL_DELAY_SAMPLES, f"{w}: correction"
+            assert abs(np.angle(r["xval"] * np.conj(o["xval"]))) < TOL_PHASE_RAD, f"{w}: phase"
+            for nm in ("xval", "xvalm1", "xvalp1"):
+                assert abs(r[nm] - o[nm]) < 1e-4 * abs(o["xval"]), f"{w}: {nm}"
+            assert abs(r["SNR"] - o["SNR"]) < TOL_SNR_DB, f"{w}: SNR {r['SNR']} vs {o['SNR']}"
+            assert abs(r["puissancecode"] - o["puissancecode"]) < TOL_SNR_DB, f"{w}: puissancecode"
+            assert abs(r["puissance"] / o["puissance"] - 1) < 1e-4, f"{w}: puissance"
+    return res
+
+
 def run_doppler_bank(lib, n=10000, nbins=16, span=2000.0, true_df=437.0, seed=3, snr_db=-10.0, check_every=1):
     """configs[3]: one record correlated over a bank of Doppler bins (the per-bin body of search_df,
     claudio_aligned_code_re_separate.m:33-42): peak index bit-exact, magnitude and metric to 1e-4."""

@@ -30,6 +30,11 @@ def test_fine_frequency_against_reference_python_outputs(name):
     pc.run_ref_py_golden(pc.EMU_LIB, name)
 
 
+@pytest.mark.parametrize("n", [10000, 200000])
+def test_cpp_program_flavour(n):
+    pc.run_variant_cpp(pc.EMU_LIB, n)
+
+
 def test_variant_g_1e6():
     pc.run_variant_g(pc.EMU_LIB, 1000000, seeds=[11])
 

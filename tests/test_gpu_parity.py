@@ -51,6 +51,12 @@ def test_against_reference_python_outputs(name):
     pc.run_ref_py_golden(pc.CUDA_LIB, name)
 
 
+@pytest.mark.parametrize("n", [200000, 5000000])
+def test_cpp_program_flavour(n):
+    """processing/CPP/main.cpp:224-361 semantics (Hamming-windowed code spectrum, given df, var/n)."""
+    pc.run_variant_cpp(pc.CUDA_LIB, n, seeds=(5, 6) if n < 5000000 else (5,))
+
+
 def test_qpsk_x4_estimator_and_complex_replica():
     """configs[2]: QPSK, x^4 estimator, 100 kchip/s code (N = 200 000)."""
     pc.run_qpsk(pc.CUDA_LIB)
