@@ -148,6 +148,17 @@ class Correlator:
                     "twstft_process_windows")
         return out
 
+    def estimate_decimated(self, iq, dec=25, foffset=0.0, remote=0):
+        """GoRanging::df (processing/CPP/main.cpp:363-450): whole-file estimator on one instant out of `dec`.
+        Returns (df[nch], pos[nch]); entries of channels not looked at (remote) stay 0 / -1."""
+        iq = np.ascontiguousarray(iq, dtype=np.int16)
+        df = np.zeros(2)
+        pos = np.full(2, -1, dtype=np.int64)
+        self._check(self.lib.twstft_estimate_decimated(self._plan, iq.ctypes.data, iq.size // (2 * self.nch), int(dec),
+                                                       float(foffset), int(remote), df.ctypes.data, pos.ctypes.data),
+                    "twstft_estimate_decimated")
+        return df[:self.nch], pos[:self.nch]
+
     def estimate_carrier(self, iq, ls=1):
         """Carrier offset of every block of ls*N sample instants (ls=2: the 2-s blocks of the K scripts)."""
         iq = np.ascontiguousarray(iq, dtype=np.int16)

@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include "backend.cuh"
 #include "k_row.cuh"
+#include "k_decim.cuh"
 #include "k_col.cuh"
 #include "k_rowcorr.cuh"
 #include "k_small.cuh"
@@ -50,7 +51,10 @@ public:
     virtual size_t bytes_per_lane() const = 0;
     virtual int setup(Backend* be, int max_lanes, int nq) = 0;
     virtual int build_code(const unsigned char* d_bits, int rep, int qpsk, float2 mean, double code_pow) = 0;
-    virtual void set_code_window(int w) = 0;   // 1: Hamming-windowed code spectrum (C++ program); before build_code
+    virtual void set_code_window(int w) = 0;
+    // forward transform of `lanes` cf32 sequences of size() points, [lane][n] -> [lane][k1][k2] (bin k1 + col_len*k2);
+    // in place allowed (d_out == d_in); lanes <= max_lanes
+    virtual int spectrum_cf32(const float2* d_in, float2* d_out, int lanes) = 0;   // 1: Hamming-windowed code spectrum (C++ program); before build_code
     virtual int estimate(const RunArgs& a, const EstimatorCfg& e) = 0;   // -> d_df/d_sbin (+ derotation tables)
     virtual int estimate_block2(const RunArgs& a, const EstimatorCfg& e) = 0;
     virtual int fine_frequency(const RunArgs& a) = 0;   // A10: d_df += dfleftover, derotation tables rebuilt
@@ -179,6 +183,22 @@ public:
             w.src = d_code; w.dst = d_code_win; w.N = N; w.N1 = L1; w.L = N2;
             be->template launch<KCodeWindow>(dim3((unsigned)((N + KCodeWindow::NT - 1) / KCodeWindow::NT), 1, 1), w);
         }
+        return be->ok() ? 0 : -1;
+    }
+
+    int spectrum_cf32(const float2* d_in, float2* d_out, int lanes) override
+    {
+        if (lanes > max_lanes) return -2;
+        ColParams c{};
+        c.src = d_in; c.dst = d_A; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.invN = 1.0 / (double)N; c.nch = 1;
+        c.nq = 1; c.ntx = NCOLTILE; c.ny = lanes;
+        typedef KCol<CS, TS, SRC_CF32, COL_FWD, 0, N2, 1> KC;
+        be->template launch<KC>(pgrid<KC>((i64)NCOLTILE * lanes), c);
+        RowParams r{};
+        r.src = d_A; r.dst = d_out; r.blob = d_blob_r; r.N = N; r.N1 = L1; r.invN = 1.0 / (double)N;
+        r.invM = 1.0 / ((double)nq * (double)N); r.nblk = NROWBLK; r.nlanes = lanes;
+        typedef KRow<RS, RPC, ROW_FWD_STORE> KR;
+        be->template launch<KR>(pgrid<KR>((i64)NROWBLK * lanes), r);
         return be->ok() ? 0 : -1;
     }
 

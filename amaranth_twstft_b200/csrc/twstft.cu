@@ -636,6 +636,97 @@ int twstft_estimate_bins(twstft_plan* p, const int16_t* iq, int iq_on_device, si
     return rc;
 }
 
+// GoRanging::df (processing/CPP/main.cpp:363-450); kernels and the L = s*M decomposition in k_decim.cuh.
+int twstft_estimate_decimated(twstft_plan* p, const int16_t* iq, size_t total_instants, int dec, double foffset,
+                              int remote, double* df, int64_t* pos)
+{
+    if (!p || !p->pipe || !iq || !df || dec < 1) return TWSTFT_E_ARG;
+    const int nch = p->nch;
+    const i64 M = p->pipe->size();
+    const i64 L = (i64)(total_instants / (size_t)dec);          // ftell/(sizeof(int16)*4*N), main.cpp:377
+    if (L < M || L % M != 0 || L / M > 32768 || L >= ((i64)1 << 32))
+        return fail(p, TWSTFT_E_SIZE, "decimated length must be a multiple (<= 32768) of the plan's window length");
+    const int s = (int)(L / M);
+    const int nuse = (nch == 2 && !remote) ? 2 : 1;
+    const double fs = p->cfg.fs;
+    p->be.use();
+    // reader: one sample instant out of `dec` (fread 4 int16, fseek the rest, main.cpp:381-397) and the exact raw sums
+    std::vector<short2> g((size_t)L * nch);
+    long long sum[2][2] = {{0, 0}, {0, 0}};
+    const short2* src = reinterpret_cast<const short2*>(iq);
+    for (i64 n = 0; n < L; n++)
+        for (int c = 0; c < nch; c++) {
+            const short2 v = src[(size_t)n * dec * nch + c];
+            g[(size_t)n * nch + c] = v;
+            sum[c][0] += v.x;
+            sum[c][1] += v.y;
+        }
+    // freq=linspace(-fs/2/N, fs/2/N, L); kmax = last i with freq<16000, kmin = last i with freq<=-16000 (:393-398)
+    const double f0 = -fs / 2 / dec, f1 = fs / 2 / dec, delta = L > 1 ? (f1 - f0) / (double)(L - 1) : 0.0;
+    auto freq_at = [&](i64 i) { return i == L - 1 ? f1 : f0 + delta * (double)i; };
+    const double frange = 8000.0;
+    i64 kmin = 0, kmax = 0;
+    for (i64 i = 0; i < L; i++) {
+        const double f = freq_at(i);
+        if (f < 2 * frange) kmax = i;
+        if (f <= -2 * frange) kmin = i;
+    }
+    if (kmax <= kmin) return fail(p, TWSTFT_E_ARG, "empty estimator window");
+    std::vector<float2> wt(s);
+    for (int j = 0; j < s; j++) {
+        const double a = -6.283185307179586476925287 * (double)j / (double)s;
+        wt[j] = make_float2((float)cos(a), (float)sin(a));
+    }
+    short2* d_g = (short2*)p->be.alloc(sizeof(short2) * g.size());
+    float2* d_G = (float2*)p->be.alloc(sizeof(float2) * (size_t)L);
+    float2* d_wt = (float2*)p->be.alloc(sizeof(float2) * s);
+    const unsigned gx = (unsigned)((M + KDecCombine::NT - 1) / KDecCombine::NT);
+    const unsigned gy = (unsigned)((s + KDecCombine::KT - 1) / KDecCombine::KT);
+    u64* d_key = (u64*)p->be.alloc(sizeof(u64) * (size_t)gx * gy);
+    int rc = TWSTFT_OK;
+    if (!p->be.ok()) rc = fail(p, TWSTFT_E_NOMEM, "device allocation failed");
+    if (rc == TWSTFT_OK) {
+        p->be.h2d(d_g, g.data(), sizeof(short2) * g.size());
+        p->be.h2d(d_wt, wt.data(), sizeof(float2) * s);
+    }
+    std::vector<u64> keys((size_t)gx * gy);
+    for (int c = 0; c < nuse && rc == TWSTFT_OK; c++) {
+        DecSquareParams q{};
+        q.g = d_g; q.nch = nch; q.ch = c; q.L = L; q.s = s; q.M = M;
+        q.mean_re = (double)sum[c][0] / (double)L; q.mean_im = (double)sum[c][1] / (double)L;
+        q.cyc_per_sample = foffset * (double)dec / fs;
+        q.dst = d_G;
+        p->be.launch<KDecSquare>(dim3((unsigned)((L + KDecSquare::NT - 1) / KDecSquare::NT), 1, 1), q);
+        for (int l0 = 0; l0 < s && rc == TWSTFT_OK; l0 += p->max_lanes) {
+            const int nl = std::min(p->max_lanes, s - l0);
+            if (p->pipe->spectrum_cf32(d_G + (size_t)l0 * M, d_G + (size_t)l0 * M, nl) != 0)
+                rc = fail(p, TWSTFT_E_CUDA, p->be.err_string());
+        }
+        DecTwiddleParams t{};
+        t.G = d_G; t.s = s; t.M = M; t.L = L; t.L1 = p->pipe->col_len(); t.N2 = p->pipe->row_len();
+        p->be.launch<KDecTwiddle>(dim3((unsigned)((M + KDecTwiddle::NT - 1) / KDecTwiddle::NT), (unsigned)s, 1), t);
+        DecCombineParams k{};
+        k.G = d_G; k.wtab = d_wt; k.s = s; k.M = M; k.L = L; k.L1 = t.L1; k.N2 = t.N2;
+        k.win_lo = c == 0 ? kmin : 0;                 // channel 1: out[kmin:kmax), channel 2: every bin (:427-445)
+        k.win_hi = c == 0 ? kmax - 1 : L - 1;
+        k.part_key = d_key;
+        p->be.launch<KDecCombine>(dim3(gx, gy, 1), k);
+        p->be.d2h(keys.data(), d_key, sizeof(u64) * keys.size());
+        p->be.sync();
+        if (!p->be.ok()) { rc = fail(p, TWSTFT_E_CUDA, p->be.err_string()); break; }
+        u64 best = 0;
+        for (u64 v : keys) best = v > best ? v : best;
+        const i64 ps = (i64)key_index(best);
+        df[c] = freq_at(ps) / 2.0 + foffset;
+        if (pos) pos[c] = ps;
+    }
+    p->be.free(d_key);
+    p->be.free(d_wt);
+    p->be.free(d_G);
+    p->be.free(d_g);
+    return rc;
+}
+
 void* twstft_host_alloc(size_t bytes)
 {
 #ifdef TWSTFT_EMU

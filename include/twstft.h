@@ -21,6 +21,7 @@
  *   twstft_search_df     k=search_df(d,k,df_threshold)                            claudio_aligned_code_re_separate.m:26-46
  *   twstft_search_df_block  the same on the 2-s block the scripts hand it                 claudio_aligned_code_re_separate.m:150
  *   twstft_estimate_bins d2=fftshift(abs(fft(d.^2))); max(d2(kbon-3:kbon+3)), d=[dold;block]  claudio_aligned_code_re_separate.m:166-168
+ *   twstft_estimate_decimated  GoRanging::df: whole-file estimator on one instant out of 25            processing/CPP/main.cpp:363-450
  *   twstft_result        one row of the .mat variables                            godual_ranging.m:128-130, lo_separate.m:166
  *
  * Conventions: plain C, caller owns every host buffer, the plan owns device memory and streams,
@@ -176,6 +177,16 @@ int twstft_estimate_bins(twstft_plan* plan, const int16_t* iq, int iq_on_device,
  * squared, window on that axis): the first radix-2 split of the 2N-point transform is fused into the loads. */
 int twstft_estimate_carrier_block(twstft_plan* plan, const int16_t* iq, int iq_on_device, size_t nblocks, int ls,
                                   double* df, int64_t* bins);
+
+/* Whole-file carrier estimator of the C++ program (GoRanging::df, processing/CPP/main.cpp:363-450) on a HOST
+ * buffer of total_instants sample instants in the plan's layout: one instant out of `dec` (25), derotated by
+ * foffset, raw mean removed, squared, ONE transform of L = total_instants/dec points per channel;
+ * freq = linspace(-fs/2/dec, fs/2/dec, L); channel 1 searches [kmin,kmax) (|f| < 16 kHz), channel 2 (remote == 0)
+ * every bin; df[ch] = freq[pos]/2 + foffset, pos[ch] = index on the fftshift'ed axis (may be NULL).
+ * The plan's window length M must divide L (L = s*M: s transforms of M points on the plan's kernels plus a direct
+ * s-point stage); TWSTFT_E_SIZE otherwise. */
+int twstft_estimate_decimated(twstft_plan* plan, const int16_t* iq, size_t total_instants, int dec, double foffset,
+                              int remote, double* df, int64_t* pos);
 
 /* Pinned host memory for the end-to-end path, device memory helpers for device-resident inputs. */
 void* twstft_host_alloc(size_t bytes);

@@ -211,16 +211,17 @@ def df_CPP(raw_file, nch_total, fs=FS, dec=25, foffset=0.0, remote=0):
     if out is None:                                                     # memcpy halves of :413-414 for odd L
         f = np.abs(_fft.fft(x1 * x1))
         h = L // 2
-        out = np.concatenate([f[h:h + h], f[:h], f[2 * h:]])
+        out = np.concatenate([f[h:h + h], f[:h], np.zeros(L - 2 * h)])      # the resize() zero stays
     pos1 = int(np.argmax(out[kmin:kmax])) + kmin
-    res = {1: freq[pos1] / 2.0 + foffset}
+    res = {1: freq[pos1] / 2.0 + foffset, "pos1": pos1}
     if remote == 0:
         x2 = (r[4 * idx + 2] + 1j * r[4 * idx + 3]) * lo
         x2 = x2 - np.mean(x2)
         f = np.abs(_fft.fft(x2 * x2))
         h = L // 2
-        out2 = np.concatenate([f[h:h + h], f[:h], f[2 * h:]])
-        res[2] = freq[int(np.argmax(out2))] / 2.0 + foffset
+        out2 = np.concatenate([f[h:h + h], f[:h], np.zeros(L - 2 * h)])
+        res["pos2"] = int(np.argmax(out2))
+        res[2] = freq[res["pos2"]] / 2.0 + foffset
     return res
 
 

@@ -35,6 +35,11 @@ def test_cpp_program_flavour(n):
     pc.run_variant_cpp(pc.EMU_LIB, n)
 
 
+@pytest.mark.parametrize("s,foffset,remote", [(3, 0.0, 0), (8, 0.0, 0), (5, 1500.0, 1)])
+def test_cpp_whole_file_estimator(s, foffset, remote):
+    pc.run_decimated_estimator(pc.EMU_LIB, m=10000, s=s, foffset=foffset, remote=remote)
+
+
 def test_variant_g_1e6():
     pc.run_variant_g(pc.EMU_LIB, 1000000, seeds=[11])
 

@@ -57,6 +57,12 @@ def test_cpp_program_flavour(n):
     pc.run_variant_cpp(pc.CUDA_LIB, n, seeds=(5, 6) if n < 5000000 else (5,))
 
 
+@pytest.mark.parametrize("m,s,foffset,remote", [(10000, 7, 0.0, 0), (200000, 6, 0.0, 0), (200000, 3, 2500.0, 1)])
+def test_cpp_whole_file_estimator(m, s, foffset, remote):
+    """GoRanging::df (processing/CPP/main.cpp:363-450): L = s*m decimated points, s sub-transforms on the plan."""
+    pc.run_decimated_estimator(pc.CUDA_LIB, m=m, s=s, foffset=foffset, remote=remote)
+
+
 def test_qpsk_x4_estimator_and_complex_replica():
     """configs[2]: QPSK, x^4 estimator, 100 kchip/s code (N = 200 000)."""
     pc.run_qpsk(pc.CUDA_LIB)
