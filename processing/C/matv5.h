@@ -38,9 +38,10 @@ static inline void mat5_pad(FILE* f, size_t bytes)
     if (bytes % 8) fwrite(z, 1, 8 - bytes % 8, f);
 }
 
-/* 1 x n double vector, im may be NULL */
-static inline int mat5_vector(FILE* f, const char* name, const double* re, const double* im, size_t n)
+/* rows x cols double matrix (column-major data), im may be NULL */
+static inline int mat5_matrix(FILE* f, const char* name, const double* re, const double* im, size_t rows, size_t cols)
 {
+    const size_t n = rows * cols;
     const size_t nl = strlen(name), nlp = (nl + 7) / 8 * 8;
     const size_t data = 8 + n * 8;           /* n*8 is already a multiple of 8 */
     const size_t total = 16 + 16 + 8 + nlp + data * (im ? 2 : 1);
@@ -49,7 +50,7 @@ static inline int mat5_vector(FILE* f, const char* name, const double* re, const
     const uint32_t flags[2] = {(uint32_t)MX_DOUBLE_CLASS | (im ? 0x0800u : 0u), 0};
     fwrite(flags, 4, 2, f);
     mat5_tag(f, MI_INT32, 8);
-    const int32_t dims[2] = {1, (int32_t)n};
+    const int32_t dims[2] = {(int32_t)rows, (int32_t)cols};
     fwrite(dims, 4, 2, f);
     mat5_tag(f, MI_INT8, (uint32_t)nl);
     fwrite(name, 1, nl, f);
@@ -61,5 +62,10 @@ static inline int mat5_vector(FILE* f, const char* name, const double* re, const
         fwrite(im, 8, n, f);
     }
     return ferror(f) ? -1 : 0;
+}
+/* 1 x n double vector, im may be NULL */
+static inline int mat5_vector(FILE* f, const char* name, const double* re, const double* im, size_t n)
+{
+    return mat5_matrix(f, name, re, im, 1, n);
 }
 #endif

@@ -76,6 +76,57 @@ def test_godual_cli_cuda(tmp_path):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# processing/C/godual_cpp.c: the C++ program's flavour (processing/CPP/main.cpp) -- whole-file estimator, Hamming-windowed
+# code spectrum, <name>C.mat with [P x 1] variables
+def _run_cpp_cli(libdir, libname, lib, tmp_path, nrec=25, remote=0):
+    exe = str(tmp_path / "godual_cpp")
+    subprocess.check_call(["gcc", "-O2", "-std=c11", "-o", exe, os.path.join(CDIR, "godual_cpp.c"), f"-L{libdir}",
+                           f"-l{libname}", f"-Wl,-rpath,{libdir}", "-lm"])
+    bits, code = pc.make_code(N)
+    recs = [synth.record_pair(code, 900 + i, ch1=dict(df=2345.6, delay=3000.0 + 0.1 * i), ch2=dict(df=-321.0))[0]
+            for i in range(nrec)]
+    data = tmp_path / "1671606372short.bin"
+    with open(data, "wb") as f:
+        for r in recs:
+            f.write(r.tobytes())
+    codef = tmp_path / "code.bin"
+    codef.write_bytes(bits.tobytes())
+    out = subprocess.run([exe, str(data), str(codef), str(remote)], capture_output=True, text=True, check=True)
+    lines = out.stdout.splitlines()
+    assert lines[-1] == "No more data" and any(ln.startswith("df1=") for ln in lines)
+    mat = scipy.io.loadmat(str(tmp_path / (("remote" if remote else "") + "1671606372shortC.mat")))
+    raw = np.concatenate(recs)
+    dfs = oc.df_CPP(raw, 2, remote=remote)
+    fw = oc.fcode_CPP(code)
+    for ch in ((1,) if remote else (1, 2)):
+        for nm in ("correction", "SNR", "df", "puissance"):
+            assert mat[f"{nm}{ch}"].shape == (nrec, 1), nm
+        assert mat[f"xval{ch}"].dtype == np.complex128 and mat[f"xval{ch}m1"].shape == (nrec, 1)
+        assert np.all(mat[f"df{ch}"][:, 0] == dfs[ch])
+        for i in (0, nrec - 1):
+            d = oc.unpack_interleaved2(recs[i])[ch - 1]
+            o = oc.processing_CPP(d, dfs[ch], fw, code)
+            assert abs(mat[f"correction{ch}"][i, 0] - o["correction"]) < 3e-4
+            assert abs(mat[f"SNR{ch}"][i, 0] - o["SNR"]) < 0.01
+            assert abs(mat[f"puissance{ch}code"][i, 0] - o["puissancecode"]) < 0.01
+            assert abs(mat[f"xval{ch}"][i, 0] - o["xval"]) < 1e-4 * abs(o["xval"])
+            assert abs(mat[f"xval{ch}p1"][i, 0] - o["xvalp1"]) < 1e-4 * abs(o["xval"])
+    if remote:
+        assert "correction2" not in mat
+
+
+@pytest.mark.skipif(not os.path.exists(pc.EMU_LIB), reason="emulation library not built")
+@pytest.mark.parametrize("remote", [0, 1])
+def test_godual_cpp_cli_emulation(tmp_path, remote):
+    _run_cpp_cli(os.path.dirname(pc.EMU_LIB), "twstft_emu", pc.EMU_LIB, tmp_path, remote=remote)
+
+
+@pytest.mark.gpu
+def test_godual_cpp_cli_cuda(tmp_path):
+    _run_cpp_cli(os.path.dirname(pc.CUDA_LIB), "twstft", pc.CUDA_LIB, tmp_path, nrec=50)
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # processing/C/claudio_aligned.c: the K-variant production loops (lo / re / ranging scripts) in C over the C ABI
 def _build_k(libdir, libname, out):
     subprocess.check_call(["gcc", "-O2", "-std=c11", "-o", out, os.path.join(CDIR, "claudio_aligned.c"), f"-L{libdir}",
