@@ -51,6 +51,30 @@ def test_against_reference_python_outputs(name):
     pc.run_ref_py_golden(pc.CUDA_LIB, name)
 
 
+def test_full_size_circular_shift_property():
+    """Size-independent property at the BASELINE size (N = 5e6).  With a derotation frequency of a whole number of
+    cycles per window the whole chain is circularly shift-equivariant: rotating the record by d samples moves the
+    peak by 3*d on the interpolated grid (mod 3N) and leaves fine delay, |xval| and SNR unchanged; the estimator's
+    magnitude spectrum, hence its arg-max, does not move (fp32 transforms: small tolerances)."""
+    n = 5000000
+    bits, code = pc.make_code(n)
+    raw, _ = synth.record_pair(code, 4242, ch1=dict(df=4321.0), ch2=dict(df=0.0))
+    d = 1234567
+    rolled = np.roll(raw.reshape(-1, 4), d, axis=0).reshape(-1)
+    both = np.concatenate([raw, rolled])
+    with Correlator(nsamples=n, max_batch=2, lib=pc.CUDA_LIB) as cor:
+        cor.set_code(bits)
+        df, bins = cor.estimate_carrier(both)
+        res = cor.process_windows(both, [0, n], [[4321.0, 0.0]] * 2)
+    assert np.array_equal(bins[0], bins[1]) and np.array_equal(df[0], df[1])
+    for ch in (0, 1):
+        a, b = res[0, ch], res[1, ch]
+        assert (int(a["indice"]) - 1 + 3 * d) % (3 * n) == int(b["indice"]) - 1
+        assert abs(a["correction"] - b["correction"]) < 3e-4
+        assert abs(pc.snr_db(a) - pc.snr_db(b)) < pc.TOL_SNR_DB
+        assert abs(abs(complex(a["xval_re"], a["xval_im"])) / abs(complex(b["xval_re"], b["xval_im"])) - 1) < 1e-4
+
+
 @pytest.mark.parametrize("n", [200000, 5000000])
 def test_cpp_program_flavour(n):
     """processing/CPP/main.cpp:224-361 semantics (Hamming-windowed code spectrum, given df, var/n)."""
