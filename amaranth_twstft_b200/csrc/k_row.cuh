@@ -212,8 +212,21 @@ template <class S, int RPC, int MODE> struct KRow {
         }
         if (S::NSTAGE == 3 && PH == 1) dif_stage_mid<S>(j, r.v, sm, acc);
         if (S::NSTAGE >= 2 && PH == S::NSTAGE - 1) {
-            dif_stage_last<S>(j, r.v, acc);
-            epilogue(p, wk, rl, j, r, gtab);
+            // estimator modes: a thread whose last-stage outputs all fall outside the window (most of them: the
+            // window is a few dozen of the L bins of a row) skips its last butterfly; whole warps drop out
+            bool need = true;
+            if (MODE != ROW_FWD_STORE) {
+                need = false;
+#pragma unroll
+                for (int b = 0; b < NBL; b++) {
+                    const int jb = j + S::NTS * b;
+                    need = need || (slot_mask(p.oa1, p.ob1, jb) | slot_mask(p.oa2, p.ob2, jb)) != 0u;
+                }
+            }
+            if (need) {
+                dif_stage_last<S>(j, r.v, acc);
+                epilogue(p, wk, rl, j, r, gtab);
+            }
         }
         if (HASFIN && PH == NCOMP) {
             if (tid == 0) {

@@ -111,6 +111,7 @@ template <class S, int RPC, int NQ> struct KRowCorr {
         u64 key;
         double dsum[NSUM];
         unsigned tmem;       // TMEM base address of this CTA (device)
+        float2 obase[(S::L / S::RLAST) / S::NTS];   // four-step twiddle base of this thread's outputs, per item
 #ifdef TWSTFT_EMU
         float2 P[S::E];      // host emulation: the parked spectrum
 #endif
@@ -242,12 +243,13 @@ template <class S, int RPC, int NQ> struct KRowCorr {
                     constexpr int q = F - 1;
                     float2* d = p.dst + (wk.lane * NQ + q) * p.N + (i64)row * S::L;
                     const float2* gr = gtab + rl * S::RLAST;
-                    float2 base[NBL];
+                    if (q == 0) {                         // the same for every polyphase of the item: computed once
 #pragma unroll
-                    for (int b = 0; b < NBL; b++)
-                        base[b] = cis_cycles((double)((i64)row * (j + S::NTS * b)) * p.invN);
+                        for (int b = 0; b < NBL; b++)
+                            r.obase[b] = cis_cycles((double)((i64)row * (j + S::NTS * b)) * p.invN);
+                    }
                     last_stage_visit<S>(j, r.v, [&](int o, float2 x, int b, int m) {
-                        d[o] = cmul(cswap(x), cmul(base[b], gr[m]));
+                        d[o] = cmul(cswap(x), cmul(r.obase[b], gr[m]));
                     });
                 }
             }
