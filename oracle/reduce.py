@@ -82,3 +82,72 @@ def one_second_rows(s, mjd0, per=25):
         rows.append((mjd0 + cpt / 86400.0, *vals))
         cpt += 1
     return rows
+
+
+# --------------------------------------------------------------------------------------------------------------
+# ORACLE (test infrastructure) for processing/C/gofinal.c: processing/Octave/gofinal_{op,ltfb}.m and tw.m restated.
+def _station(mat, cflavour, two):
+    """gofinal_ltfb.m:35-47 / gofinal_op.m:30-43: solutions, SNR (dB) and df of one result file."""
+    g = lambda k: np.asarray(mat[k], dtype=float).ravel()
+    corr = lambda c: g(f"correction{c}_a") if f"correction{c}_a" in mat else g(f"correction{c}")
+    out = {}
+    for c in ((1, 2) if two else (1,)):
+        if cflavour:
+            out[f"sol{c}"], out[f"snr{c}"] = corr(c), g(f"SNR{c}")
+        else:
+            out[f"sol{c}"], out[f"snr{c}"] = g(f"indice{c}") + corr(c), 10 * np.log10(g(f"SNR{c}r") + g(f"SNR{c}i"))
+        out[f"df{c}"] = g(f"df{c}")
+    out["codelen"] = len(g("code")) if "code" in mat else 5000000
+    return out
+
+
+def gofinal_rows(local, remote, end_epoch, ltfb, local_c=False, remote_c=False, fs=5e6):
+    """Rows (epoch, 9 values) written by gofinal_op.m:70-78 (every record) / gofinal_ltfb.m:84-90 (selected)."""
+    lo, re = _station(local, local_c, True), _station(remote, remote_c, False)
+    n = len(lo["sol1"])
+    dateini = end_epoch - n
+    ind = np.nonzero(lo["snr1"] > lo["snr1"].max() - 10)[0]
+    res = (lo["sol1"][ind] - lo["sol2"][ind]) / fs / 3
+    x = np.arange(1, len(res) + 1, dtype=float)
+    fit = lambda r, xx: r - np.polyval(np.polyfit(xx - xx.mean(), r - r.mean(), 2), xx - xx.mean()) - r.mean()
+    r = fit(res, x)
+    if np.std(r, ddof=1) > 1e-6 and len(res) >= 150:
+        i1 = np.nonzero(np.abs(res - res[29:40].mean()) < 1e-5)[0]
+        i2 = np.nonzero(np.abs(res - res[139:150].mean()) < 1e-5)[0]
+        if len(i1) and len(i2):
+            ind = i1 if len(i1) > len(i2) else i2            # indices into the filtered list (the script's quirk)
+            res = res[ind]
+            r = fit(res, np.arange(1, len(res) + 1, dtype=float))
+    stats = (float(np.std(r * 1e9, ddof=1)), float(res.mean() + (1 if res.mean() < 0 else 0)))
+    step = (lo["codelen"] / 2) / 2.5e6
+    rows = []
+    for p in (ind if ltfb else range(n)):
+        rows.append((int(np.floor(dateini + p * step)), lo["sol1"][p] / 3 / fs, lo["df1"][p], lo["snr1"][p],
+                     lo["sol2"][p] / 3 / fs, lo["df2"][p], lo["snr2"][p], re["sol1"][p] / 3 / fs, re["df1"][p], re["snr1"][p]))
+    return rows, stats
+
+
+def two_way(op, lt):
+    """tw.m:16-50 on the two numeric tables (15 columns): returns (difference, std_ns, mean_ns, n) or (difference,)."""
+    stamp = lambda t: ((((t[0, 1] * 31 + t[0, 2]) * 24) + t[0, 3] * 60) + t[0, 4] * 60) + t[0, 5]
+    a, b = stamp(op), stamp(lt)
+    d = int(abs(a - b))
+    if a > b:
+        lt = lt[d:]
+    else:
+        op = op[d:]
+    m = min(len(op), len(lt))
+    op, lt = op[:m], lt[:m]
+    if d >= 180 or m == 0:
+        return (d,)
+    for first in ("lt", "op"):
+        t = lt if first == "lt" else op
+        k = np.nonzero(t[:, 8] > t[:, 8].max() - 10)[0]
+        k = np.arange(k[0] + 1, k[-1])
+        lt, op = lt[k], op[k]
+    x, y = lt[:, 9] - lt[:, 12], op[:, 9] - op[:, 12]
+    x = x + (1 if x.mean() < 0 else 0)
+    y = y + (1 if y.mean() < 0 else 0)
+    res = 0.5 * (x - y)
+    res = res[np.abs(res) < 1e-6] * 1e9
+    return d, float(np.std(res, ddof=1)), float(res.mean()), len(res)
