@@ -114,7 +114,7 @@ def test_two_way_combination(exe, tmp_path):
         t[:, 6] = 0.5
         return t
     op = table(END, 170, 0.2500003, 0.7253001, -5.0)
-    lt = table(END + 7, 170, 0.7253004, 0.2500001, -6.0)      # mean(l10-l13) > 0, op wraps by +1 s
+    lt = table(END + 7, 170, 0.7747005, 0.2500001, -6.0)      # l10-l13 = 0.5247004; op wraps by +1 s to 0.5247002
     for name, t in (("a.b.c.txt", op), ("x_ltfb.txt", lt)):
         with open(tmp_path / name, "w") as f:
             f.write("% y  m  d  h  m  s\tdelay\r\n")
