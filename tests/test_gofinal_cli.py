@@ -127,4 +127,4 @@ def test_two_way_combination(exe, tmp_path):
     assert f"diff={d}" in out and d == 7
     assert abs(float(out.split("std=")[1].split()[0]) - std) < 1e-5
     assert abs(float(out.split("mean=")[1].split()[0]) - mean) < 1e-5
-    assert int(out.split("n=")[1]) == n
+    assert int(out.split("\nn=")[1]) == n
