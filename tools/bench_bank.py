@@ -1,0 +1,29 @@
+#!/usr/bin/env python3
+"""Secondary measurement (BASELINE.json configs[3]): one 1-s record correlated over a 64-bin Doppler bank +-2 kHz
+(twstft_doppler_bank, host record, single channel of the two-channel layout counted once per bin and channel).
+Prints one JSON line: records/s and achieved GB/s against SURVEY 8d's 60*N bytes per bin."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from amaranth_twstft_b200.api import Correlator
+from amaranth_twstft_b200 import synth
+
+N, NB = 5000000, 64
+cor = Correlator(nsamples=N, max_batch=16)
+bits = cor.gen_code(22, 3)
+code = 2.0 * np.repeat(bits.astype(np.float64), 2) - 1.0
+raw = synth.record_pair(code, 20261017, ch1=dict(df=437.0, snr_db=-10.0))[0]
+dfs = np.linspace(-2000.0, 2000.0, NB)
+for _ in range(2):
+    res = cor.doppler_bank(raw, dfs)
+reps = 5
+cor.timer_start()
+for _ in range(reps):
+    res = cor.doppler_bank(raw, dfs)
+ms = cor.timer_stop() / reps
+best = int(np.argmax(res["metric"][:, 0]))
+lanes = NB * 2
+print(json.dumps({"metric": "64-bin Doppler bank, 1-s 5 MS/s two-channel record (configs[3])", "ms_per_record": ms,
+                  "records_per_s": 1e3 / ms, "bins": NB, "channels": 2,
+                  "survey_bytes": 60 * N * lanes, "gbs_survey_bytes": 60 * N * lanes / (ms * 1e-3) / 1e9,
+                  "best_bin_hz": float(dfs[best]), "true_df_hz": 437.0}))
