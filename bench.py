@@ -32,10 +32,15 @@ RECORDS_PER_STEP = 16
 METRIC = "two-channel 1-s 5 MS/s records correlated per second"
 UNIT = "records/s"
 SURVEY_BYTES_PER_RECORD = 1.4e9  # 140*N bytes per channel, two channels
-# algorithmic bytes per lane (one channel of one record) and launch, in units of N bytes
-ALG_BYTES_N = {"mean": 4, "col_fwd_raw": 12, "row_fwd_argmax": 8, "row_corr": 32, "col_inv_argmax": 24}
+# ALGORITHMIC bytes per lane (one channel of one record) and launch, in units of N bytes: SURVEY.md section 8d's
+# budget, item by item (mean 4N; x^p FFT 12N + 8N; derotate+FFT pass-1 12N; pass-2 32N + IFFT pass-1 32N = the work
+# of row_corr; IFFT pass-2 24N; the 16N of the SNR dot product have no kernel here: spectral identity).
+ALG_BYTES_N = {"mean": 4, "col_fwd_raw": 12, "row_fwd_argmax": 8, "row_corr": 64, "col_inv_argmax": 24}
+# bytes this design actually has to MOVE per lane and launch: row_corr keeps the product
+# spectrum and ffty on chip (tensor memory) and shares the code row through L2, 32N instead of 64N
+MOVED_BYTES_N = {"mean": 4, "col_fwd_raw": 12, "row_fwd_argmax": 8, "row_corr": 32, "col_inv_argmax": 24}
 LAUNCHES_PER_LANE = {"col_fwd_raw": 2}          # estimator pass + derotated pass
-ALG_TOTAL_N = sum(v * LAUNCHES_PER_LANE.get(k, 1) for k, v in ALG_BYTES_N.items())   # 92
+ALG_TOTAL_N = sum(v * LAUNCHES_PER_LANE.get(k, 1) for k, v in MOVED_BYTES_N.items())   # 92
 
 
 def measured_peak():
@@ -294,6 +299,9 @@ def main():
             ent["alg_bytes"] = b
             ent["gbs"] = b / (avg * 1e-3) / 1e9
             ent["frac"] = ent["gbs"] / peak
+            mb = MOVED_BYTES_N[name] * N * 2 * R
+            ent["moved_bytes"] = mb
+            ent["frac_moved"] = mb / (avg * 1e-3) / 1e9 / peak
         kernels[name] = ent
     tot = sum(v[0] for v in prof.values()) or 1.0
     for name in kernels:
@@ -310,8 +318,13 @@ def main():
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
                     "frac": kernels[dom]["frac"], "traffic": traffic, "peak_kind": peak_kind,
                     "share_of_step": kernels[dom]["share"],
-                    "note": "achieved = algorithmic bytes of the launch / CUDA-event duration; the kernel is FP32-pipe "
-                            "bound (fma pipe ~50% busy, profiles/), not HBM bound"}
+                    "alg_bytes_per_launch": kernels[dom]["alg_bytes"],
+                    "moved_bytes_per_launch": kernels[dom]["moved_bytes"],
+                    "frac_on_bytes_moved": kernels[dom]["frac_moved"],
+                    "note": "achieved = SURVEY 8d algorithmic bytes of the launch (64N per channel for row_corr: "
+                            "pass-2 + IFFT pass-1) / CUDA-event duration.  The fused kernel keeps the product spectrum "
+                            "and ffty on chip and moves 32N (ncu traffic agrees): frac_on_bytes_moved is the DRAM "
+                            "share actually used; the kernel is FP32-pipe bound (fma pipe ~50% busy, profiles/)"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -323,8 +336,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": R * rec_bytes,
                     "d2h_bytes_per_step": int(res_e2e.nbytes)},
             "roofline": roofline, "kernels": kernels,
-            "pipeline": {"alg_bytes_per_record": ALG_TOTAL_N * N * 2,
-                         "frac_of_hbm_peak": value / world * ALG_TOTAL_N * N * 2 / 1e9 / peak,
+            "pipeline": {"moved_bytes_per_record": ALG_TOTAL_N * N * 2,
+                         "frac_of_hbm_peak_bytes_moved": value / world * ALG_TOTAL_N * N * 2 / 1e9 / peak,
                          "survey_bytes_per_record": SURVEY_BYTES_PER_RECORD,
                          "frac_of_hbm_peak_survey_bytes": value / world * SURVEY_BYTES_PER_RECORD / 1e9 / peak}}
 
