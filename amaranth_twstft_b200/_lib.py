@@ -23,7 +23,7 @@ EXPORTS = [
     "twstft_host_free", "twstft_device_alloc", "twstft_device_free", "twstft_copy_to_device",
     "twstft_copy_to_host", "twstft_synchronize", "twstft_kernel_launches", "twstft_debug_fetch",
     "twstft_window_bins", "twstft_doppler_bank", "twstft_search_df", "twstft_estimate_carrier_block", "twstft_estimate_bins",
-    "twstft_search_df_block", "twstft_estimate_decimated", "twstft_timer_start", "twstft_timer_stop", "twstft_profile_enable", "twstft_profile_read",
+    "twstft_search_df_block", "twstft_estimate_decimated", "twstft_fast_counters", "twstft_timer_start", "twstft_timer_stop", "twstft_profile_enable", "twstft_profile_read",
 ]
 
 
@@ -32,7 +32,7 @@ class Config(C.Structure):
         ("fs", C.c_double), ("nsamples", C.c_int64), ("samples_per_chip", C.c_int), ("variant", C.c_int),
         ("modulation", C.c_int), ("nint", C.c_int), ("layout", C.c_int), ("freq_axis", C.c_int),
         ("win_lo_hz", C.c_double), ("win_hi_hz", C.c_double), ("est_sub_mean", C.c_int), ("ddof", C.c_int),
-        ("max_batch", C.c_int), ("device_id", C.c_int), ("fine_freq", C.c_int), ("code_window", C.c_int),
+        ("max_batch", C.c_int), ("device_id", C.c_int), ("fine_freq", C.c_int), ("code_window", C.c_int), ("fast_peak", C.c_int),
     ]
 
 
@@ -86,6 +86,7 @@ def load(path=None):
     lib.twstft_estimate_carrier_block.argtypes = [P, P, C.c_int, C.c_size_t, C.c_int, P, P]
     lib.twstft_search_df_block.argtypes = [P, P, P, C.c_int, C.c_int, C.c_double, P, P, P]
     lib.twstft_estimate_bins.argtypes = [P, P, C.c_int, C.c_size_t, C.c_int64, C.c_int, P]
+    lib.twstft_fast_counters.argtypes = [P, P, P]
     lib.twstft_estimate_decimated.argtypes = [P, P, C.c_size_t, C.c_int, C.c_double, C.c_int, P, P]
     lib.twstft_host_alloc.argtypes = [C.c_size_t]
     lib.twstft_host_alloc.restype = P

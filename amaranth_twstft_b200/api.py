@@ -30,7 +30,7 @@ class Correlator:
 
     def __init__(self, nsamples=5000000, fs=5e6, variant="G", modulation="bpsk", layout="interleaved2",
                  window_hz=(-20000.0, 20000.0), freq_axis=None, nint=1, samples_per_chip=2, ddof=1,
-                 est_sub_mean=None, max_batch=4, device=0, lib=None, fine_freq=False, code_window=False):
+                 est_sub_mean=None, max_batch=4, device=0, lib=None, fine_freq=False, code_window=False, fast_peak=False):
         self.lib = _lib.load(lib)
         cfg = _lib.Config()
         self.lib.twstft_default_config(C.byref(cfg))
@@ -51,6 +51,7 @@ class Correlator:
         cfg.device_id = device
         cfg.fine_freq = int(bool(fine_freq))
         cfg.code_window = int(bool(code_window))     # 1: Hamming (processing/CPP/main.cpp:717-719)
+        cfg.fast_peak = int(bool(fast_peak))
         self.cfg = cfg
         self.nch = 2 if cfg.layout == _lib.LAYOUT_INTERLEAVED2 else 1
         self.N = int(nsamples)
@@ -93,6 +94,13 @@ class Correlator:
     @property
     def kernel_launches(self):
         return int(self.lib.twstft_kernel_launches(self._plan))
+
+    @property
+    def fast_counters(self):
+        """(records through the fast peak path, records re-run through the full path)"""
+        a, b = C.c_int64(), C.c_int64()
+        self.lib.twstft_fast_counters(self._plan, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def window_bins(self):
         lo, hi = C.c_int64(), C.c_int64()

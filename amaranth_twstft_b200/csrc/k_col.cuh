@@ -18,7 +18,9 @@
 namespace twstft {
 
 enum ColSrc { SRC_RAW = 0, SRC_CF32 = 1, SRC_BITS = 2 };
-enum ColMode { COL_FWD = 0, COL_INV_ARGMAX = 1, COL_INV_STORE = 2, COL_INV_ARGMAX_STATS = 3 };
+enum ColMode { COL_FWD = 0, COL_INV_ARGMAX = 1, COL_INV_STORE = 2, COL_INV_ARGMAX_STATS = 3, COL_INV_ARGMAX_K2 = 4 };
+// COL_INV_ARGMAX_K2: besides the tile's first maximum, the maximum over the tile's rows OTHER than the row of that
+// maximum (part_key2) -- the "everything else" bound of the fast peak path (k_fast.cuh).
 
 struct ColParams {
     const void* src;
@@ -50,6 +52,7 @@ struct ColParams {
     int nq;
     u64* part_key;         // [y][ntx]
     double* part_stat;     // COL_INV_ARGMAX_STATS: [y][ntx][2]  sum|z|, sum|z|^2 of the tile
+    u64* part_key2;        // COL_INV_ARGMAX_K2: [y][ntx]
 };
 
 // N2C / NCH: row length and channel count as compile-time constants (0 = take them from Params), so that
@@ -59,6 +62,7 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
     static const char* name()
     {
         return MODE == COL_INV_ARGMAX ? "col_inv_argmax" : MODE == COL_INV_ARGMAX_STATS ? "col_inv_argmax_stats"
+             : MODE == COL_INV_ARGMAX_K2 ? "col_inv_argmax_k2"
              : MODE == COL_INV_STORE ? "col_inv_store"
              : SRC == SRC_RAW ? "col_fwd_raw" : SRC == SRC_BITS ? "col_fwd_bits" : "col_fwd_cf32";
     }
@@ -72,14 +76,16 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
     static constexpr int OFF_DATA = OFF_G + ((NG + 1) & ~1);
     static constexpr int NCOMP = S::NSTAGE == 1 ? 2 : S::NSTAGE;
     static constexpr bool STATS = (MODE == COL_INV_ARGMAX_STATS);
-    static constexpr bool HASFIN = (MODE == COL_INV_ARGMAX || STATS);
-    static constexpr int NPH = NCOMP + (HASFIN ? 1 : 0);
+    static constexpr bool K2 = (MODE == COL_INV_ARGMAX_K2);
+    static constexpr bool HASFIN = (MODE == COL_INV_ARGMAX || STATS || K2);
+    static constexpr int NPH = NCOMP + (HASFIN ? 1 : 0) + (K2 ? 1 : 0);
     static constexpr int NSUM = STATS ? 2 : 1;
     static constexpr int NBL = (S::L / S::RLAST) / S::NTS;
     static constexpr int NB0 = S::SP0 / S::NTS;
     struct Regs {
         float2 v[S::E];
         u64 key;
+        u64 key1;             // K2: the tile maximum while `key` is reused for the second search
         double dsum[NSUM];
     };
     static HD constexpr size_t smem_bytes()
@@ -88,6 +94,7 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
     }
     static HD constexpr int sync_after(int ph)
     {
+        if (K2 && ph == NCOMP) return SYNC_MAXKEY;
         return (ph == NCOMP - 1 && HASFIN) ? (STATS ? SYNC_MAXKEY_SUMD : SYNC_MAXKEY) : SYNC_BARRIER;
     }
     static HD int n2of(const Params& p) { return N2C > 0 ? N2C : n2of(p); }
@@ -266,7 +273,31 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
             dif_stage_last<S>(j, r.v, acc);
             epilogue(p, wk, s, j, r, gtab);
         }
-        if (HASFIN && PH == NCOMP) {
+        if (K2 && PH == NCOMP) {
+            // second search: this thread's outputs outside the row of the tile maximum (values are still in r.v)
+            r.key1 = r.key;
+            const unsigned rowlen = (unsigned)p.nq * (unsigned)n2of(p);
+            const int row1 = (int)(key_index(r.key) / rowlen);
+            const int q = wk.y % p.nq;
+            const int col = wk.x * TS + s;
+            u64 best = 0;
+            last_stage_visit<S>(j, r.v, [&](int, float2 x, int b, int m) {
+                const int c = S::NTS * b + m * S::NSLAST;
+                if (j + c != row1) {
+                    const unsigned idx = (unsigned)p.nq * (unsigned)col + (unsigned)q + rowlen * (unsigned)(j + c);
+                    const u64 k = make_key(cnorm(x), idx);
+                    best = k > best ? k : best;
+                }
+            });
+            r.key = best;
+        }
+        if (K2 && PH == NCOMP + 1) {
+            if (tid == 0) {
+                p.part_key[(i64)wk.y * p.ntx + wk.x] = r.key1;
+                p.part_key2[(i64)wk.y * p.ntx + wk.x] = r.key;
+            }
+        }
+        if (!K2 && HASFIN && PH == NCOMP) {
             if (tid == 0) {
                 p.part_key[(i64)wk.y * p.ntx + wk.x] = r.key;
                 if (STATS) {

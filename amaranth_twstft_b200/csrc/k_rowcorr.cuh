@@ -78,6 +78,8 @@ struct RowCorrParams {
     int conj_mode;           // 0: Y*conj(C) (variant G)   1: conj(Y)*C (variant K)
     double* part_energy;     // [lane][nblk]  sum |Y|^2
     float2* y0;              // [lane] Y[0]
+    float2* pdst;            // optional [lane][N1][L]: the product spectrum P (fast peak path, k_fast.cuh)
+    double* part_penergy;    // with pdst: [lane][nblk] sum |P|^2
 };
 
 template <class S, int RPC, int NQ> struct KRowCorr {
@@ -102,7 +104,8 @@ template <class S, int RPC, int NQ> struct KRowCorr {
     static constexpr int OFF_G = OFF_QC + NQC;
     static constexpr int OFF_DATA = OFF_G + ((NG + 1) & ~1);
     static constexpr int NPH = NST * (1 + NQ);
-    static constexpr int NSUM = 1;
+    static constexpr bool PSTORE = (NQ == 1);     // the product spectrum can be stored by the 1x kernel only
+    static constexpr int NSUM = PSTORE ? 2 : 1;
     static constexpr int NBL = (S::L / S::RLAST) / S::NTS;
     static constexpr int NB0 = S::SP0 / S::NTS;
     static_assert(NBL == NB0, "butterflies per thread must match between the first and the last stage");
@@ -177,6 +180,7 @@ template <class S, int RPC, int NQ> struct KRowCorr {
         if (PH == 0) {
             r.key = 0;
             r.dsum[0] = 0.0;
+            if (PSTORE) r.dsum[NSUM - 1] = 0.0;
             if (active) {
                 for (int t = tid; t < NG; t += NTA) {      // conjugate four-step twiddle steps of this item's rows
                     const int rl2 = t / S::RLAST, m = t % S::RLAST;
@@ -206,7 +210,10 @@ template <class S, int RPC, int NQ> struct KRowCorr {
             constexpr int q = F - 1;
             if (q > 0) fetch(r);                          // q == 0: P is still in v
             if (active) {
-                if (q == 0 && tid == 0) p.part_energy[wk.lane * p.nblk + wk.rowblk] = r.dsum[0];
+                if (q == 0 && tid == 0) {
+                    p.part_energy[wk.lane * p.nblk + wk.rowblk] = r.dsum[0];
+                    if (PSTORE && p.pdst) p.part_penergy[wk.lane * p.nblk + wk.rowblk] = r.dsum[NSUM - 1];
+                }
 #pragma unroll
                 for (int b = 0; b < NB0; b++) {
                     if (q == 0) {
@@ -229,16 +236,20 @@ template <class S, int RPC, int NQ> struct KRowCorr {
             if (active) {
                 dif_stage_last<S>(j, r.v, acc);
                 if (F == 0) {
-                    float e = 0.f;
+                    float e = 0.f, e2 = 0.f;
                     const int cm = p.conj_mode;
+                    float2* pd = (PSTORE && p.pdst) ? p.pdst + wk.lane * p.N + (i64)row * S::L : nullptr;
                     const float2* c = p.code + (i64)row * S::L;
                     if (row == 0 && j == 0) p.y0[wk.lane] = r.v[0];
                     last_stage_visit<S>(j, r.v, [&](int o, float2 x, int b, int m) {
                         const float2 cc = c[o];
                         e += cnorm(x);
-                        r.v[b * S::R0 + m] = cm ? cmul(cconj(x), cc) : cmulc(x, cc);
+                        const float2 pr = cm ? cmul(cconj(x), cc) : cmulc(x, cc);
+                        r.v[b * S::R0 + m] = pr;
+                        if (PSTORE && pd) { pd[o] = pr; e2 += cnorm(pr); }
                     });
                     r.dsum[0] = (double)e;
+                    if (PSTORE) r.dsum[NSUM - 1] = (double)e2;
                 } else {
                     constexpr int q = F - 1;
                     float2* d = p.dst + (wk.lane * NQ + q) * p.N + (i64)row * S::L;

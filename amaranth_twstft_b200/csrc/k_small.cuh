@@ -351,6 +351,7 @@ struct PeakEvalParams {
     i64* p0_out;           // [lane]
     double* part;          // [lane][NPTS][2]
     const i64* p0_in;      // optional [lane]: evaluate around this index instead of the tiles' maximum
+    int npts_rt, dlo_rt;   // npts_rt > 0: grid.x = npts_rt lags starting at p0 + dlo_rt (instead of NPTS / DLO)
 };
 // One CTA per (lag, lane): prnmap[p] = sum_k1 B[q][k1][n2] exp(+2 pi i k1 n1 / L1) with
 // p = nq*(n1*N2 + n2) + q, i.e. one output of the inverse column transform evaluated directly
@@ -378,7 +379,7 @@ template <int NPTS, int DLO> struct KPeakEvalT {
         } else if (PH == 1) {
             const i64 M = (i64)p.nq * p.N;
             const i64 p0 = p.p0_in ? p.p0_in[lane] : (i64)key_index(r.key);
-            i64 pp = (p0 + DLO + d) % M;
+            i64 pp = (p0 + (p.npts_rt ? p.dlo_rt : DLO) + d) % M;
             if (pp < 0) pp += M;
             const int q = (int)(pp % p.nq);
             const i64 m = pp / p.nq;
@@ -394,8 +395,9 @@ template <int NPTS, int DLO> struct KPeakEvalT {
             r.dsum[0] = sr;
             r.dsum[1] = si;
         } else if (tid == 0) {
-            p.part[(lane * NPTS + d) * 2] = r.dsum[0];
-            p.part[(lane * NPTS + d) * 2 + 1] = r.dsum[1];
+            const int np = p.npts_rt ? p.npts_rt : NPTS;
+            p.part[(lane * np + d) * 2] = r.dsum[0];
+            p.part[(lane * np + d) * 2 + 1] = r.dsum[1];
             if (d == 0 && !p.p0_in) p.p0_out[lane] = (i64)key_index(r.key);
         }
     }
@@ -432,6 +434,7 @@ struct PeakFinParams {
     double code_pow;           // mean |code|^2 (sum|yincode|^2 = code_pow * sum|yint|^2)
     Result* out;               // [lane]
     i64* pc_out;               // optional [lane]: the decided 0-based peak index
+    const int* fail;           // optional [lane]: fast peak path not certified -> status bit 2 (the host re-runs the record)
     int snr_only;              // 1: the lags are those of the UNWINDOWED correlation around the already decided
                                //    peak p0 (C++ flavour, processing/CPP/main.cpp:319-357): only the SNR / power
                                //    fields of `out` are rewritten
@@ -520,6 +523,7 @@ struct KPeakFinal {
         o.puissancecode = mr * mr + mi * mi;
         o.puissancenoise = var_c;
         o.carrier_bin = (double)p.sbin[lane];
+        if (p.fail && p.fail[lane]) o.status += 4.0;
         p.out[lane] = o;
     }
 };

@@ -9,7 +9,7 @@
 
 namespace twstft {
 
-constexpr int RED_SCRATCH_BYTES = 32 * 8 * 16;   // 32 warps x up to 16 doubles
+constexpr int RED_SCRATCH_BYTES = 32 * 8 * 20;   // 32 warps x up to 20 doubles
 
 #ifdef __CUDACC__
 template <class K> __device__ __forceinline__ void block_max_key(typename K::Regs& r, unsigned char* scratch)
@@ -34,6 +34,7 @@ template <class K> __device__ __forceinline__ void block_max_key(typename K::Reg
 
 template <class K> __device__ __forceinline__ void block_sum_d(typename K::Regs& r, unsigned char* scratch)
 {
+    static_assert(K::NSUM * 32 * 8 <= RED_SCRATCH_BYTES, "reduction scratch too small for this kernel's sums");
     double* s = reinterpret_cast<double*>(scratch);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int NW = (K::NT + 31) / 32;

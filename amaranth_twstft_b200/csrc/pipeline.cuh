@@ -14,6 +14,7 @@
 #include "backend.cuh"
 #include "k_row.cuh"
 #include "k_decim.cuh"
+#include "k_fast.cuh"
 #include "k_col.cuh"
 #include "k_rowcorr.cuh"
 #include "k_small.cuh"
@@ -40,6 +41,7 @@ struct RunArgs {
     int ddof;
     double fs;
     Result* d_out;             // [lanes]
+    int allow_fast;            // the caller re-runs rows flagged status bit 2 through the full path (k_fast.cuh)
 };
 
 class IPipe {
@@ -52,6 +54,7 @@ public:
     virtual int setup(Backend* be, int max_lanes, int nq) = 0;
     virtual int build_code(const unsigned char* d_bits, int rep, int qpsk, float2 mean, double code_pow) = 0;
     virtual void set_code_window(int w) = 0;
+    virtual int set_fast_peak(int on) = 0;     // fast peak path (k_fast.cuh): 0 ok, <0 allocation failure
     // forward transform of `lanes` cf32 sequences of size() points, [lane][n] -> [lane][k1][k2] (bin k1 + col_len*k2);
     // in place allowed (d_out == d_in); lanes <= max_lanes
     virtual int spectrum_cf32(const float2* d_in, float2* d_out, int lanes) = 0;   // 1: Hamming-windowed code spectrum (C++ program); before build_code
@@ -92,7 +95,8 @@ public:
         if (!be) return;
         void* all[] = {d_blob_c, d_blob_r, d_code, d_qconst, d_A, d_B, d_sums, d_energy, d_df, d_peakpart,
                        d_keyrow, d_keycol, d_sbin, d_p0, d_y0, d_lrow, d_lcol, d_stat, d_bankpart, d_ang, d_finepart,
-                       d_code_win};
+                       d_code_win, d_P, d_R2, d_U2, d_keycol2, d_fn, d_fbase, d_fa2, d_ffail, d_penergy, d_spart,
+                       d_lagpart, d_hbtab, d_fwork};
         for (void* p : all) be->free(p);
     }
     i64 size() const override { return N; }
@@ -157,6 +161,67 @@ public:
         d_y0 = dalloc<float2>(lanes);
         d_lrow = dalloc<float2>((size_t)lanes * L1);
         d_lcol = dalloc<float2>((size_t)lanes * N2);
+        return be->ok() ? 0 : -1;
+    }
+
+    // ---- fast peak path (k_fast.cuh): one inverse transform + exact local lags + a bound on everything else
+    int fast_peak = 0;
+    double fast_H = 0.0, fast_T = 0.0;
+    float2 *d_P = nullptr, *d_R2 = nullptr, *d_U2 = nullptr;
+    u64* d_keycol2 = nullptr;
+    i64 *d_fn = nullptr, *d_fbase = nullptr;
+    double *d_fa2 = nullptr, *d_penergy = nullptr, *d_spart = nullptr, *d_lagpart = nullptr, *d_hbtab = nullptr, *d_fwork = nullptr;
+    int* d_ffail = nullptr;
+    static double fast_hb(double t, double n)
+    {
+        const double s = fabs(sin(3.14159265358979323846 * t / n));
+        return 0.86602540378443865 / (n * s);
+    }
+    int set_fast_peak(int on) override
+    {
+        if (!on || nq != 3) { fast_peak = 0; return 0; }
+        if (!d_P) {
+            const double n = (double)N;
+            const i64 K = N / 4 < 100000 ? N / 4 : 100000;
+            for (int q = 1; q <= 2; q++) {
+                double h = 0.0, t2 = 0.0;
+                for (i64 d = -(N / 2); d < N - N / 2; d++) {
+                    const double v = fast_hb(fabs((double)d + q / 3.0), n);
+                    if (d >= -K && d <= K) h += v; else t2 += v * v;
+                }
+                if (h > fast_H) fast_H = h;
+                if (sqrt(t2) > fast_T) fast_T = sqrt(t2);
+            }
+            std::vector<float2> u2(N2);
+            for (int k2 = 0; k2 < N2; k2++) {
+                const double c = ((double)L1 * k2 - (k2 >= N2 / 2 ? n : 0.0)) / (3.0 * n);
+                const double a = 6.283185307179586476925287 * (c - floor(c));
+                u2[k2] = make_float2((float)cos(a), (float)sin(a));
+            }
+            const int ns = 3 * TSI, ntab = 2 * ns + 5;
+            std::vector<double> hbt(2 * (size_t)ntab);
+            for (int q = 1; q <= 2; q++)
+                for (int dd = -(ns + 2); dd <= ns + 2; dd++)
+                    hbt[(size_t)(q - 1) * ntab + dd + ns + 2] = fast_hb(fabs((double)dd + q / 3.0), n);
+            d_hbtab = dalloc<double>(hbt.size());
+            d_fwork = dalloc<double>((size_t)max_lanes * 8);
+            d_P = dalloc<float2>((size_t)max_lanes * N);
+            d_R2 = dalloc<float2>((size_t)max_lanes * N2);
+            d_U2 = dalloc<float2>(N2);
+            d_keycol2 = dalloc<u64>((size_t)max_lanes * NCOLTILE_I);
+            d_fn = dalloc<i64>(max_lanes);
+            d_fbase = dalloc<i64>(max_lanes);
+            d_fa2 = dalloc<double>(max_lanes);
+            d_ffail = dalloc<int>(max_lanes);
+            d_penergy = dalloc<double>((size_t)max_lanes * NROWBLK);
+            d_spart = dalloc<double>((size_t)max_lanes * 3 * TSI * 2);
+            d_lagpart = dalloc<double>((size_t)max_lanes * L1 * 2 * FAST_NLAG);
+            if (!be->ok()) return -1;
+            be->h2d(d_U2, u2.data(), sizeof(float2) * N2);
+            be->h2d(d_hbtab, hbt.data(), sizeof(double) * hbt.size());
+            be->sync();
+        }
+        fast_peak = 1;
         return be->ok() ? 0 : -1;
     }
 
@@ -431,6 +496,7 @@ public:
         r.invN = 1.0 / (double)N; r.invM = 1.0 / ((double)nq * (double)N); r.nlanes = lanes; r.nblk = NROWBLK;
         r.conj_mode = a.variant; r.part_energy = d_energy; r.y0 = d_y0;
         if (code_window && d_code_win) r.code = d_code_win;
+        if (fast_peak && a.allow_fast && nq == 3 && !(code_window && d_code_win)) return correlate_fast(a, r);
         auto row_corr = [&]() {
             i64 g = (i64)NROWBLK * lanes;
             typedef KRowCorr<RS, RPC, 3> K3;
@@ -466,6 +532,47 @@ public:
             pf.snr_only = 1; pf.pc_out = nullptr;
             be->template launch<KPeakFinal>(dim3(1, lanes, 1), pf);
         }
+        return be->ok() ? 0 : -1;
+    }
+
+    // fast peak path (k_fast.cuh); `r` prepared by correlate()
+    int correlate_fast(const RunArgs& a, RowCorrParams r)
+    {
+        const int lanes = a.nrec * a.nch;
+        typedef KRowCorr<RS, RPC, 1> K1;
+        r.pdst = d_P; r.part_penergy = d_penergy;
+        i64 g = (i64)NROWBLK * lanes;
+        if (g > (i64)be->num_sms * K1::MINB) g = (i64)be->num_sms * K1::MINB;
+        be->template launch<K1>(dim3((unsigned)g, 1, 1), r);
+        ColParams c{};
+        c.src = d_B; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.invN = 1.0 / (double)N; c.nch = 1; c.nq = 1;
+        c.part_key = d_keycol; c.part_key2 = d_keycol2; c.ntx = NCOLTILE_I; c.ny = lanes;
+        typedef KCol<CS, TSI, SRC_CF32, COL_INV_ARGMAX_K2, 0, N2, 1> KC2;
+        be->template launch<KC2>(pgrid<KC2>((i64)c.ntx * c.ny), c);
+        FastPrepParams fp{};
+        fp.key1 = d_keycol; fp.key2 = d_keycol2; fp.ntile = NCOLTILE_I; fp.tsi = TSI; fp.N2 = N2;
+        fp.nstar = d_fn; fp.base = d_fbase; fp.a2 = d_fa2; fp.fail = d_ffail;
+        be->template launch<KFastPrep>(dim3(1, lanes, 1), fp);
+        PeakEvalParams pe{};
+        pe.part_key = d_keycol; pe.npart = 0; pe.B = d_B; pe.N = N; pe.nq = 1; pe.L1 = L1; pe.N2 = N2;
+        pe.p0_out = d_p0; pe.part = d_spart; pe.p0_in = d_fbase; pe.npts_rt = 3 * TSI; pe.dlo_rt = 0;
+        be->template launch<KPeakEval>(dim3(3 * TSI, lanes, 1), pe);
+        LagTabParams lt{};
+        lt.nstar = d_fn; lt.N2 = N2; lt.R2 = d_R2;
+        be->template launch<KLagTables>(dim3((N2 + KLagTables::NT - 1) / KLagTables::NT, lanes, 1), lt);
+        LagPParams lp{};
+        lp.P = d_P; lp.R2 = d_R2; lp.U2 = d_U2; lp.nstar = d_fn; lp.N = N; lp.L1 = L1; lp.N2 = N2; lp.part = d_lagpart;
+        be->template launch<KLagP>(dim3(L1, lanes, 1), lp);
+        FastCertParams fc{};
+        fc.lagpart = d_lagpart; fc.L1 = L1; fc.spart = d_spart; fc.ns = 3 * TSI; fc.nstar = d_fn; fc.base = d_fbase;
+        fc.a2 = d_fa2; fc.penergy = d_penergy; fc.nen = NROWBLK; fc.N = N; fc.H = fast_H; fc.T = fast_T;
+        fc.fail = d_ffail; fc.p0 = d_p0; fc.part7 = d_peakpart; fc.hbtab = d_hbtab; fc.work = d_fwork;
+        be->template launch<KFastCert>(dim3(1, lanes, 1), fc);
+        PeakFinParams pf{};
+        pf.part = d_peakpart; pf.nblk = 1; pf.part_energy = d_energy; pf.nen = NROWBLK; pf.y0 = d_y0;
+        pf.code_pow = code_pow; pf.p0 = d_p0; pf.df = d_df; pf.sbin = d_sbin; pf.N = N; pf.nq = nq; pf.variant = a.variant;
+        pf.ddof = a.ddof; pf.out = a.d_out; pf.fail = d_ffail;
+        be->template launch<KPeakFinal>(dim3(1, lanes, 1), pf);
         return be->ok() ? 0 : -1;
     }
 

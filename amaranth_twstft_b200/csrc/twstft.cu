@@ -30,6 +30,7 @@ struct twstft_plan {
     i64* d_off = nullptr;
     unsigned char* d_bits = nullptr;
     size_t bits_cap = 0;
+    long long fast_records = 0, fast_rerun = 0;   // records through the fast peak path / re-run through the full path
     std::string err;
 };
 
@@ -83,6 +84,7 @@ void twstft_default_config(twstft_config* c)
     c->device_id = 0;
     c->fine_freq = 0;
     c->code_window = TWSTFT_CODEWIN_NONE;
+    c->fast_peak = 0;
 }
 
 int twstft_plan_create(const twstft_config* cfg, twstft_plan** out)
@@ -108,6 +110,8 @@ int twstft_plan_create(const twstft_config* cfg, twstft_plan** out)
     p->max_lanes = cfg->max_batch * p->nch;
     if (p->pipe->setup(&p->be, p->max_lanes, p->nq) != 0)
         return fail(p, TWSTFT_E_NOMEM, std::string("device allocation failed: ") + p->be.err_string());
+    if (cfg->fast_peak && p->pipe->set_fast_peak(1) != 0)
+        return fail(p, TWSTFT_E_NOMEM, std::string("device allocation failed (fast peak path): ") + p->be.err_string());
     const i64 N = cfg->nsamples;
     p->raw_elems_per_rec = (size_t)N * p->nch;
     p->d_res = (Result*)p->be.alloc(sizeof(Result) * p->max_lanes);
@@ -148,6 +152,14 @@ void twstft_plan_destroy(twstft_plan* p)
 }
 
 const char* twstft_last_error(const twstft_plan* p) { return p ? p->err.c_str() : "null plan"; }
+
+int twstft_fast_counters(const twstft_plan* p, int64_t* records, int64_t* rerun)
+{
+    if (!p) return TWSTFT_E_ARG;
+    if (records) *records = p->fast_records;
+    if (rerun) *rerun = p->fast_rerun;
+    return TWSTFT_OK;
+}
 
 int64_t twstft_kernel_launches(const twstft_plan* p) { return p ? p->be.launches : 0; }
 
@@ -279,6 +291,35 @@ static int ensure_raw(twstft_plan* p)
     return p->be.ok() ? 0 : -1;
 }
 
+// Fast peak path (k_fast.cuh): rows whose certificate failed carry status bit 2; those records go through the full
+// three-polyphase path here, one at a time (rare: records without a correlation peak).  `src` host or device.
+static int rerun_uncertified(twstft_plan* p, const short2* src, bool on_device, size_t nrecords, twstft_result* results)
+{
+    p->fast_records += (long long)nrecords;
+    for (size_t r = 0; r < nrecords; r++) {
+        bool flagged = false;
+        for (int c = 0; c < p->nch; c++) flagged = flagged || (((int)results[r * p->nch + c].status) & 4);
+        if (!flagged) continue;
+        p->fast_rerun++;
+        const short2* d = src + r * p->raw_elems_per_rec;
+        if (!on_device) {
+            p->be.h2d(p->d_raw, d, sizeof(short2) * p->raw_elems_per_rec);
+            d = p->d_raw;
+        }
+        RunArgs a{};
+        a.d_raw = d; a.nrec = 1; a.nch = p->nch; a.rec_stride = (i64)p->raw_elems_per_rec; a.d_rec_offset = nullptr;
+        a.estimate = 1; a.variant = p->cfg.variant; a.ddof = p->cfg.ddof; a.fs = p->cfg.fs; a.d_out = p->d_res;
+        a.allow_fast = 0;
+        if (p->pipe->estimate(a, p->est) != 0) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
+        if (p->cfg.fine_freq && p->pipe->fine_frequency(a) != 0) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
+        if (p->pipe->correlate(a) != 0) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
+        p->be.d2h(results + r * p->nch, p->d_res, sizeof(Result) * p->nch);
+        p->be.sync();
+        if (!p->be.ok()) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
+    }
+    return TWSTFT_OK;
+}
+
 // records resident on the device, contiguous
 static int process_dev(twstft_plan* p, const short2* d_iq, size_t nrecords, twstft_result* results)
 {
@@ -289,6 +330,7 @@ static int process_dev(twstft_plan* p, const short2* d_iq, size_t nrecords, twst
         a.d_raw = d_iq + r0 * p->raw_elems_per_rec;
         a.nrec = nb; a.nch = p->nch; a.rec_stride = (i64)p->raw_elems_per_rec; a.d_rec_offset = nullptr;
         a.estimate = 1; a.variant = p->cfg.variant; a.ddof = p->cfg.ddof; a.fs = p->cfg.fs; a.d_out = p->d_res;
+        a.allow_fast = p->cfg.fast_peak;
         if (p->pipe->estimate(a, p->est) != 0) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
         if (p->cfg.fine_freq) {
             const int frc = p->pipe->fine_frequency(a);
@@ -301,6 +343,7 @@ static int process_dev(twstft_plan* p, const short2* d_iq, size_t nrecords, twst
         p->be.sync();
         if (!p->be.ok()) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
     }
+    if (p->cfg.fast_peak) return rerun_uncertified(p, d_iq, true, nrecords, results);
     return TWSTFT_OK;
 }
 
@@ -346,6 +389,7 @@ int twstft_process(twstft_plan* p, const int16_t* iq, size_t nrecords, twstft_re
         a.d_raw = d; a.nrec = (int)nb; a.nch = p->nch; a.rec_stride = (i64)p->raw_elems_per_rec; a.d_rec_offset = nullptr;
         a.estimate = 1; a.variant = p->cfg.variant; a.ddof = p->cfg.ddof; a.fs = p->cfg.fs;
         a.d_out = p->d_res + r0 * p->nch;
+        a.allow_fast = p->cfg.fast_peak;
         if (p->pipe->estimate(a, p->est) != 0) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
         if (p->cfg.fine_freq) {
             const int frc = p->pipe->fine_frequency(a);
@@ -359,6 +403,7 @@ int twstft_process(twstft_plan* p, const int16_t* iq, size_t nrecords, twstft_re
     p->be.d2h(results, p->d_res, sizeof(Result) * nrecords * p->nch);
     p->be.sync();
     if (!p->be.ok()) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
+    if (p->cfg.fast_peak) return rerun_uncertified(p, h, false, nrecords, results);
     return TWSTFT_OK;
 }
 

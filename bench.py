@@ -39,8 +39,14 @@ ALG_BYTES_N = {"mean": 4, "col_fwd_raw": 12, "row_fwd_argmax": 8, "row_corr": 64
 # bytes this design actually has to MOVE per lane and launch: row_corr keeps the product
 # spectrum and ffty on chip (tensor memory) and shares the code row through L2, 32N instead of 64N
 MOVED_BYTES_N = {"mean": 4, "col_fwd_raw": 12, "row_fwd_argmax": 8, "row_corr": 32, "col_inv_argmax": 24}
+# fast peak path (k_fast.cuh, default): one inverse transform; row_corr reads A 8N, writes B 8N and P 8N; the column
+# pass reads 8N and does the job SURVEY budgets at 24N; the exact lags around the maximum read P once more (8N)
+ALG_BYTES_N_FAST = {"mean": 4, "col_fwd_raw": 12, "row_fwd_argmax": 8, "row_corr": 64, "col_inv_argmax_k2": 24}
+MOVED_BYTES_N_FAST = {"mean": 4, "col_fwd_raw": 12, "row_fwd_argmax": 8, "row_corr": 24, "col_inv_argmax_k2": 8,
+                      "fast_lag_p": 8}
 LAUNCHES_PER_LANE = {"col_fwd_raw": 2}          # estimator pass + derotated pass
 ALG_TOTAL_N = sum(v * LAUNCHES_PER_LANE.get(k, 1) for k, v in MOVED_BYTES_N.items())   # 92
+ALG_TOTAL_N_FAST = sum(v * LAUNCHES_PER_LANE.get(k, 1) for k, v in MOVED_BYTES_N_FAST.items())   # 76
 
 
 def measured_peak():
@@ -209,6 +215,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--records-per-step", type=int, default=RECORDS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fast-peak", action="store_true",
+                    help="three-polyphase inverse for every record instead of the certified one-transform peak path")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -238,7 +246,11 @@ def main():
     from amaranth_twstft_b200.api import Correlator
     R = args.records_per_step
     numa = bind_to_gpu_numa(local)
-    cor = Correlator(nsamples=N, fs=FS, max_batch=R, device=local)
+    fast = not args.no_fast_peak
+    alg_n = ALG_BYTES_N_FAST if fast else ALG_BYTES_N
+    moved_n = MOVED_BYTES_N_FAST if fast else MOVED_BYTES_N
+    moved_total_n = ALG_TOTAL_N_FAST if fast else ALG_TOTAL_N
+    cor = Correlator(nsamples=N, fs=FS, max_batch=R, device=local, fast_peak=fast)
     assert cor.backend == "cuda"
     bits = cor.gen_code(CODE[0], CODE[1])
     code = 2.0 * np.repeat(bits.astype(np.float64), 2) - 1.0
@@ -294,19 +306,19 @@ def main():
     for name, (tot_ms, cnt) in prof.items():
         avg = tot_ms / max(cnt, 1)
         ent = {"avg_ms": avg, "launches": cnt, "share": None}
-        if name in ALG_BYTES_N:
-            b = ALG_BYTES_N[name] * N * 2 * R
+        if name in alg_n or name in moved_n:
+            b = alg_n.get(name, 0) * N * 2 * R
             ent["alg_bytes"] = b
             ent["gbs"] = b / (avg * 1e-3) / 1e9
             ent["frac"] = ent["gbs"] / peak
-            mb = MOVED_BYTES_N[name] * N * 2 * R
+            mb = moved_n.get(name, 0) * N * 2 * R
             ent["moved_bytes"] = mb
             ent["frac_moved"] = mb / (avg * 1e-3) / 1e9 / peak
         kernels[name] = ent
     tot = sum(v[0] for v in prof.values()) or 1.0
     for name in kernels:
         kernels[name]["share"] = prof[name][0] / tot
-    dom = max((k for k in kernels if "gbs" in kernels[k]), key=lambda k: prof[k][0], default=None)
+    dom = max((k for k in kernels if kernels[k].get("alg_bytes")), key=lambda k: prof[k][0], default=None)
     roofline = None
     if dom:
         traffic = None          # dram bytes per launch from the committed ncu --set full capture (profiles/)
@@ -330,14 +342,17 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: two-channel 1-s 5 MS/s BPSK records, 22-bit taps-3 code, x3 interpolation",
-                       "records_per_step": R, "samples_per_record": N, "l2": f"inputs larger than L2: {R} distinct "
+                       "records_per_step": R, "samples_per_record": N,
+                       "peak_path": "one inverse transform + exact local lags + certificate (k_fast.cuh), uncertified "
+                                    "records re-run in full" if fast else "three-polyphase inverse", "l2": f"inputs larger than L2: {R} distinct "
                        f"records = {R * rec_bytes / 1e6:.0f} MB raw, {R * 2 * 200:.0f} MB intermediates per step", "host_numa": numa},
             "clocks": clocks, "gpu_launches": launches,
+            "fast_peak": dict(zip(("records", "rerun_in_full"), cor.fast_counters)) if fast else None,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": R * rec_bytes,
                     "d2h_bytes_per_step": int(res_e2e.nbytes)},
             "roofline": roofline, "kernels": kernels,
-            "pipeline": {"moved_bytes_per_record": ALG_TOTAL_N * N * 2,
-                         "frac_of_hbm_peak_bytes_moved": value / world * ALG_TOTAL_N * N * 2 / 1e9 / peak,
+            "pipeline": {"moved_bytes_per_record": moved_total_n * N * 2,
+                         "frac_of_hbm_peak_bytes_moved": value / world * moved_total_n * N * 2 / 1e9 / peak,
                          "survey_bytes_per_record": SURVEY_BYTES_PER_RECORD,
                          "frac_of_hbm_peak_survey_bytes": value / world * SURVEY_BYTES_PER_RECORD / 1e9 / peak}}
 

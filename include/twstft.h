@@ -90,6 +90,11 @@ typedef struct twstft_config {
                            the peak decided on the windowed correlation, and `puissance` is sum|fft(y)|^2
                            (main.cpp:295) instead of var(y).  Scales stay Octave's (ifft 1/n): FFTW's unnormalised
                            values are 3N times xval*, and the stored correction1 is indice-1+correction */
+    int fast_peak;      /* 1: twstft_process / twstft_process_device find the interpolated maximum from ONE inverse
+                           transform plus exactly evaluated lags around its maximum, guarded by a rigorous bound on
+                           every other interpolated sample; records that fail the bound (no correlation peak) are
+                           re-run through the full three-transform path, so results are identical (k_fast.cuh).
+                           Needs nint = 1 and code_window = NONE; +8N bytes of device memory per lane */
 } twstft_config;
 
 /* One row of the reference's result variables, per channel and record (all doubles). */
@@ -205,6 +210,7 @@ int twstft_profile_enable(twstft_plan* plan, int on);
 int twstft_profile_read(twstft_plan* plan, int slot, char* name, size_t name_cap, double* total_ms, int64_t* count);
 
 /* Introspection used by tests and the benchmark. */
+int twstft_fast_counters(const twstft_plan* plan, int64_t* records, int64_t* rerun); /* fast peak path: records seen / re-run in full */
 int64_t twstft_kernel_launches(const twstft_plan* plan);   /* kernels launched so far by this plan */
 int twstft_debug_fetch(twstft_plan* plan, int what, int lane, void* host_out, size_t bytes);
 int twstft_window_bins(const twstft_plan* plan, int64_t* lo, int64_t* hi);

@@ -58,13 +58,19 @@ def make_code(n):
     return bits, oc.code_bpsk(bits)
 
 
-def run_variant_g(lib, n, seeds, fs=5e6, window=(-20000.0, 20000.0), max_batch=2, overrides=None):
-    """Two-channel interleaved records through twstft_process vs godual_ranging.m semantics."""
+def run_variant_g(lib, n, seeds, fs=5e6, window=(-20000.0, 20000.0), max_batch=2, overrides=None, fast=False):
+    """Two-channel interleaved records through twstft_process vs godual_ranging.m semantics.
+    fast: the one-transform peak path with its certificate (k_fast.cuh); results must not change."""
     bits, code = make_code(n)
     recs = [synth.record_pair(code, s, fs=fs, **(overrides or {}))[0] for s in seeds]
-    with Correlator(nsamples=n, fs=fs, window_hz=window, max_batch=max_batch, lib=lib) as cor:
+    with Correlator(nsamples=n, fs=fs, window_hz=window, max_batch=max_batch, lib=lib, fast_peak=fast) as cor:
         cor.set_code(bits)
         res = cor.process(np.stack(recs))
+        if fast:
+            seen, rerun = cor.fast_counters
+            assert seen == len(recs)
+            # the certificate needs processing gain: at N = 1e4 (40 dB) the bound is close to the peak and may fail
+            assert rerun == 0 or n < 100000, f"fast peak path not certified: {cor.fast_counters}"
     freq = oc.freq_axis_G(fs, n)
     k = oc.window(freq, window[0], window[1])
     fcode = oc.fcode_G(code)
@@ -210,6 +216,39 @@ def run_decimated_estimator(lib, m=10000, s=3, dec=25, foffset=0.0, remote=0, df
         assert int(pos[1]) == ref["pos2"], f"channel 2 position {pos[1]} vs {ref['pos2']}"
         assert abs(df[1] - ref[2]) < 1e-9 * max(1.0, abs(ref[2])), (df[1], ref[2])
     return df, pos
+
+
+def run_fast_peak_fallback(lib, n, seed=31):
+    """Fast peak path on records WITHOUT a correlation peak (noise only, and a tone): the certificate must fail, the
+    record is re-run through the full path, and the rows equal those of a plan without the fast path bit for bit;
+    a normal record in the same batch is certified (status bit 2 clear in both)."""
+    bits, code = make_code(n)
+    rng = np.random.default_rng(seed)
+    noise = np.rint(rng.normal(0, 3000, 4 * n)).astype(np.int16)
+    good = synth.record_pair(code, seed)[0]
+    t = np.arange(n)
+    tone = np.rint(2000 * np.exp(2j * np.pi * 0.01234 * t))
+    tone_rec = np.empty(4 * n, dtype=np.int16)
+    tone_rec[0::4], tone_rec[1::4] = tone.real, tone.imag
+    tone_rec[2::4], tone_rec[3::4] = noise[2::4], noise[3::4]
+    recs = np.stack([noise, good, tone_rec])
+    out, counters = {}, None
+    for fast in (False, True):
+        with Correlator(nsamples=n, max_batch=2, lib=lib, fast_peak=fast) as cor:
+            cor.set_code(bits)
+            out[fast] = cor.process(recs)
+            if fast:
+                counters = cor.fast_counters
+    assert counters[0] == 3 and counters[1] >= 1, counters       # the noise-only record cannot be certified
+    assert not np.any(out[True]["status"].astype(int) & 4)
+    for i in range(3):
+        for ch in (0, 1):
+            a, b = out[False][i, ch], out[True][i, ch]
+            assert int(a["indice"]) == int(b["indice"]), (i, ch)
+            assert a["df"] == b["df"] and a["carrier_bin"] == b["carrier_bin"]
+            assert abs(a["correction"] - b["correction"]) < 3e-4, (i, ch)
+            assert abs(snr_db(a) - snr_db(b)) < TOL_SNR_DB, (i, ch)
+    return out
 
 
 def run_doppler_bank(lib, n=10000, nbins=16, span=2000.0, true_df=437.0, seed=3, snr_db=-10.0, check_every=1):

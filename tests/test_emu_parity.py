@@ -40,6 +40,15 @@ def test_cpp_whole_file_estimator(s, foffset, remote):
     pc.run_decimated_estimator(pc.EMU_LIB, m=10000, s=s, foffset=foffset, remote=remote)
 
 
+@pytest.mark.parametrize("n", [10000, 200000, 250000])
+def test_fast_peak_path_matches_the_oracle(n):
+    pc.run_variant_g(pc.EMU_LIB, n, seeds=(11, 12, 13), fast=True)
+
+
+def test_fast_peak_path_falls_back_without_a_peak():
+    pc.run_fast_peak_fallback(pc.EMU_LIB, 10000)
+
+
 def test_variant_g_1e6():
     pc.run_variant_g(pc.EMU_LIB, 1000000, seeds=[11])
 

@@ -51,6 +51,16 @@ def test_against_reference_python_outputs(name):
     pc.run_ref_py_golden(pc.CUDA_LIB, name)
 
 
+@pytest.mark.parametrize("n", [200000, 250000, 1000000, 5000000])
+def test_fast_peak_path_matches_the_oracle(n):
+    """One inverse transform + exact local lags + certificate (k_fast.cuh): same rows as the oracle, all certified."""
+    pc.run_variant_g(pc.CUDA_LIB, n, seeds=(11, 12) if n >= 1000000 else (11, 12, 13), fast=True)
+
+
+def test_fast_peak_path_falls_back_without_a_peak():
+    pc.run_fast_peak_fallback(pc.CUDA_LIB, 250000)
+
+
 def test_full_size_circular_shift_property():
     """Size-independent property at the BASELINE size (N = 5e6).  With a derotation frequency of a whole number of
     cycles per window the whole chain is circularly shift-equivariant: rotating the record by d samples moves the
