@@ -127,24 +127,32 @@ struct KLagP {
         const i64 lane = blk.y;
         const int k1 = blk.x;
         if (PH == 0) {
-            float2 acc[FAST_NLAG];
+            // a*w^j and a*conj(w^j) share their products: with w^j = c + i s,  a w = a c + i (a s),  a conj(w) = a c - i (a s);
+            // accumulate Sr = sum a c and Ss = sum a s (one packed FMA each) and combine once at the end
+            float2 sr[4], ss[4];
 #pragma unroll
-            for (int s = 0; s < FAST_NLAG; s++) acc[s] = make_float2(0.f, 0.f);
+            for (int s = 0; s < 4; s++) sr[s] = ss[s] = make_float2(0.f, 0.f);
             const float2* row = p.P + (lane * p.L1 + k1) * (i64)p.N2;
             const float2* r2 = p.R2 + lane * p.N2;
 #pragma unroll 4
             for (int k2 = tid; k2 < p.N2; k2 += NT) {
                 const float2 a = cmul(row[k2], r2[k2]);
-                const float2 w1 = p.U2[k2];
-                const float2 w2 = cmul(w1, w1), w4 = cmul(w2, w2), w5 = cmul(w4, w1);
-                acc[0] = cadd(acc[0], cmul(a, w1));
-                acc[1] = cadd(acc[1], cmul(a, w2));
-                acc[2] = cadd(acc[2], cmul(a, w4));
-                acc[3] = cadd(acc[3], cmul(a, w5));
-                acc[4] = cadd(acc[4], cmulc(a, w1));
-                acc[5] = cadd(acc[5], cmulc(a, w2));
-                acc[6] = cadd(acc[6], cmulc(a, w4));
-                acc[7] = cadd(acc[7], cmulc(a, w5));
+                float2 w[4];
+                w[0] = p.U2[k2];
+                w[1] = cmul(w[0], w[0]);
+                w[2] = cmul(w[1], w[1]);
+                w[3] = cmul(w[2], w[0]);
+#pragma unroll
+                for (int s = 0; s < 4; s++) {
+                    sr[s] = caxpy(w[s].x, a, sr[s]);
+                    ss[s] = caxpy(w[s].y, a, ss[s]);
+                }
+            }
+            float2 acc[FAST_NLAG];
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                acc[s] = cadd(sr[s], rot_pi(ss[s]));
+                acc[s + 4] = csub(sr[s], rot_pi(ss[s]));
             }
 #pragma unroll
             for (int s = 0; s < FAST_NLAG; s++) { r.dsum[2 * s] = (double)acc[s].x; r.dsum[2 * s + 1] = (double)acc[s].y; }

@@ -307,13 +307,16 @@ def main():
         avg = tot_ms / max(cnt, 1)
         ent = {"avg_ms": avg, "launches": cnt, "share": None}
         if name in alg_n or name in moved_n:
-            b = alg_n.get(name, 0) * N * 2 * R
+            # bytes the kernel has to move for the algorithm it executes -> achieved GB/s
+            b = moved_n.get(name, 0) * N * 2 * R
             ent["alg_bytes"] = b
             ent["gbs"] = b / (avg * 1e-3) / 1e9
             ent["frac"] = ent["gbs"] / peak
-            mb = moved_n.get(name, 0) * N * 2 * R
-            ent["moved_bytes"] = mb
-            ent["frac_moved"] = mb / (avg * 1e-3) / 1e9 / peak
+            # the share of SURVEY 8d's 140N budget that this kernel's job stands for (fusion / the fast peak path
+            # remove traffic the budget counts, so this can exceed the bytes moved)
+            sb = alg_n.get(name, 0) * N * 2 * R
+            ent["survey_budget_bytes"] = sb
+            ent["frac_survey_budget"] = sb / (avg * 1e-3) / 1e9 / peak
         kernels[name] = ent
     tot = sum(v[0] for v in prof.values()) or 1.0
     for name in kernels:
@@ -331,12 +334,15 @@ def main():
                     "frac": kernels[dom]["frac"], "traffic": traffic, "peak_kind": peak_kind,
                     "share_of_step": kernels[dom]["share"],
                     "alg_bytes_per_launch": kernels[dom]["alg_bytes"],
-                    "moved_bytes_per_launch": kernels[dom]["moved_bytes"],
-                    "frac_on_bytes_moved": kernels[dom]["frac_moved"],
-                    "note": "achieved = SURVEY 8d algorithmic bytes of the launch (64N per channel for row_corr: "
-                            "pass-2 + IFFT pass-1) / CUDA-event duration.  The fused kernel keeps the product spectrum "
-                            "and ffty on chip and moves 32N (ncu traffic agrees): frac_on_bytes_moved is the DRAM "
-                            "share actually used; the kernel is FP32-pipe bound (fma pipe ~50% busy, profiles/)"}
+                    "survey_budget_bytes_per_launch": kernels[dom]["survey_budget_bytes"],
+                    "frac_survey_budget": kernels[dom]["frac_survey_budget"],
+                    "pipeline_survey_formula": {"achieved": value / world * SURVEY_BYTES_PER_RECORD / 1e9,
+                                                "frac": value / world * SURVEY_BYTES_PER_RECORD / 1e9 / peak,
+                                                "what": "SURVEY 8d: records/s per GPU x 1.4e9 B / peak"},
+                    "note": "achieved = bytes this kernel must move for the algorithm it executes / CUDA-event "
+                            "duration (ncu traffic agrees).  SURVEY 8d budgets more for the same job (product spectrum "
+                            "and ffty through HBM, three polyphase inverses): frac_survey_budget and the pipeline "
+                            "formula count that budget.  The transforms are FP32-pipe bound (profiles/), not HBM bound"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,

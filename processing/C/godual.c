@@ -49,6 +49,7 @@ int main(int argc, char** argv)
     twstft_default_config(&cfg);
     cfg.nsamples = (int64_t)nchips * cfg.samples_per_chip;
     cfg.max_batch = batch > 0 ? batch : 8;
+    cfg.fast_peak = 1;     /* one inverse transform + certificate; uncertified records are re-run in full: same rows */
     if (remote) { cfg.win_lo_hz = 80000.0; cfg.win_hi_hz = 120000.0; }
     twstft_plan* plan = NULL;
     int rc = twstft_plan_create(&cfg, &plan);

@@ -39,7 +39,7 @@ def _run_cli(exe, tmp_path, lib, remote=0):
     assert len(rows) == 3 and all(len(r) == (5 if remote else 9) for r in rows)
     mat = scipy.io.loadmat(str(tmp_path / (("remote" if remote else "") + "1671606372short.mat")))
     win = (80000.0, 120000.0) if remote else (-20000.0, 20000.0)
-    with Correlator(nsamples=N, window_hz=win, max_batch=2, lib=lib) as cor:
+    with Correlator(nsamples=N, window_hz=win, max_batch=2, lib=lib, fast_peak=True) as cor:   # like godual.c
         cor.set_code(bits)
         ref = cor.process(np.stack(recs))
     for ch in ((1,) if remote else (1, 2)):
