@@ -9,7 +9,8 @@ from amaranth_twstft_b200 import synth
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 passes = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 N = 5000000
-cor = Correlator(nsamples=N, max_batch=R)
+fast = os.environ.get('TWSTFT_PROF_FAST', '1') != '0'
+cor = Correlator(nsamples=N, max_batch=R, fast_peak=fast)   # the bench's default peak path
 bits = cor.gen_code(22, 3)
 code = 2.0 * np.repeat(bits.astype(np.float64), 2) - 1.0
 rec = synth.record_pair(code, 20261017)[0]
