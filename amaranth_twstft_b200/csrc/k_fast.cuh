@@ -31,11 +31,11 @@ struct FastPrepParams {
     const u64* key1;       // [lane][ntile] tile maxima of the 1x correlation (index = n)
     const u64* key2;       // [lane][ntile] maxima over the rows other than the row of key1
     int ntile, tsi;        // tiles per row, columns per tile
-    int N2;
+    int N2, nrow;          // row length, rows (N = N2 * nrow)
     i64* nstar;            // [lane] 1x arg-max
-    i64* base;             // [lane] first sample of S = row(n*), columns tsi*(t*-1) .. tsi*(t*+2)-1
+    i64* base;             // [lane] first sample of S = the three column tiles around n* in linear time (may span two rows)
     double* a2;            // [lane] largest |z| outside S (unnormalised units of the inverse transform)
-    int* fail;             // [lane] 1: S would leave the row -> full path
+    int* fail;             // [lane] 1: S would wrap around the array ends -> full path
 };
 struct KFastPrep {
     typedef FastPrepParams Params;
@@ -57,23 +57,25 @@ struct KFastPrep {
         } else if (PH == 1) {
             r.kmax = r.key;
             const i64 ns = (i64)key_index(r.key);
-            const int ts = (int)((ns % p.N2) / p.tsi);
-            const i64 rs = ns / p.N2;
+            const i64 base = (ns / p.tsi) * p.tsi - p.tsi;           // S = [base, base + 3 tsi) in linear time
             u64 best = 0;
             for (int t = tid; t < p.ntile; t += NT) {
                 u64 k = k1[t];
-                if (t >= ts - 1 && t <= ts + 1 && (i64)key_index(k) / p.N2 == rs) k = k2[t];
+                for (int c = 0; c < 3; c++) {                        // the three (row, tile) cells that make up S
+                    const i64 b = base + (i64)c * p.tsi;
+                    if (b >= 0 && t == (int)((b % p.N2) / p.tsi) && (i64)key_index(k) / p.N2 == b / p.N2) k = k2[t];
+                }
                 const u64 v = (k >> 32) << 32;              // compare magnitudes only
                 best = v > best ? v : best;
             }
             r.key = best;
         } else if (tid == 0) {
             const i64 ns = (i64)key_index(r.kmax);
-            const int ts = (int)((ns % p.N2) / p.tsi);
+            const i64 base = (ns / p.tsi) * p.tsi - p.tsi;
             p.nstar[lane] = ns;
-            p.base[lane] = (ns / p.N2) * p.N2 + (i64)p.tsi * (ts - 1);
+            p.base[lane] = base < 0 ? 0 : base;
             p.a2[lane] = sqrt((double)key_value(r.key));
-            p.fail[lane] = (ts < 1 || ts > p.ntile - 2) ? 1 : 0;
+            p.fail[lane] = (base < 0 || base + 3 * (i64)p.tsi > (i64)p.N2 * p.nrow) ? 1 : 0;   // S would wrap the array
         }
     }
 };

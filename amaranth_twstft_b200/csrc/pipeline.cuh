@@ -550,7 +550,7 @@ public:
         typedef KCol<CS, TSI, SRC_CF32, COL_INV_ARGMAX_K2, 0, N2, 1> KC2;
         be->template launch<KC2>(pgrid<KC2>((i64)c.ntx * c.ny), c);
         FastPrepParams fp{};
-        fp.key1 = d_keycol; fp.key2 = d_keycol2; fp.ntile = NCOLTILE_I; fp.tsi = TSI; fp.N2 = N2;
+        fp.key1 = d_keycol; fp.key2 = d_keycol2; fp.ntile = NCOLTILE_I; fp.tsi = TSI; fp.N2 = N2; fp.nrow = L1;
         fp.nstar = d_fn; fp.base = d_fbase; fp.a2 = d_fa2; fp.fail = d_ffail;
         be->template launch<KFastPrep>(dim3(1, lanes, 1), fp);
         PeakEvalParams pe{};
