@@ -67,14 +67,22 @@ struct KMean {
                 const int4* s4 = reinterpret_cast<const int4*>(s);
                 const i64 nquad = p.nelem >> 2;
                 int q0x = 0, q0y = 0, q1x = 0, q1y = 0;
-#pragma unroll 8
-                for (i64 e = e0; e < nquad; e += stride) {
-                    const int4 v = s4[e];
+                auto add = [&](const int4 v) {
                     q0x += (int)(short)(v.x & 0xffff) + (int)(short)(v.z & 0xffff);
                     q0y += (v.x >> 16) + (v.z >> 16);
                     q1x += (int)(short)(v.y & 0xffff) + (int)(short)(v.w & 0xffff);
                     q1y += (v.y >> 16) + (v.w >> 16);
+                };
+                i64 e = e0;
+                constexpr int UB = 8;                         // eight independent 16-byte loads in flight per thread
+                for (; e + (UB - 1) * stride < nquad; e += UB * stride) {
+                    int4 v[UB];
+#pragma unroll
+                    for (int u = 0; u < UB; u++) v[u] = s4[e + u * stride];
+#pragma unroll
+                    for (int u = 0; u < UB; u++) add(v[u]);
                 }
+                for (; e < nquad; e += stride) add(s4[e]);
                 if (p.nch == 2) { a0x = q0x; a0y = q0y; a1x = q1x; a1y = q1y; }
                 else { a0x = (i64)q0x + q1x; a0y = (i64)q0y + q1y; }
             } else {
