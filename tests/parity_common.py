@@ -81,7 +81,7 @@ def run_variant_g(lib, n, seeds, fs=5e6, window=(-20000.0, 20000.0), max_batch=2
     return res
 
 
-def run_ref_py_golden(lib, name):
+def run_ref_py_golden(lib, name, fast=False):
     """The library with fine_freq=1, ddof=0 against the committed outputs of the reference's OWN numpy correlator
     (experiments/221219_twoway/processing/godual_ranging.py `processing()`, run unmodified by tools/make_golden.py)
     on the same seeded records; phase (not returned by that function) against the oracle."""
@@ -98,7 +98,8 @@ def run_ref_py_golden(lib, name):
         assert hashlib.sha256(raw.tobytes()).hexdigest() == rec["sha256"], "synthetic generator drifted"
         recs.append(raw)
     w = g["window_hz"]
-    with Correlator(nsamples=n, fs=fs, window_hz=(-w, w), ddof=0, fine_freq=True, max_batch=2, lib=lib) as cor:
+    with Correlator(nsamples=n, fs=fs, window_hz=(-w, w), ddof=0, fine_freq=True, max_batch=2, lib=lib,
+                    fast_peak=fast) as cor:
         cor.set_code(bits)
         res = cor.process(np.stack(recs))
     freq = oc.freq_axis_G(fs, n)
@@ -122,14 +123,14 @@ def run_ref_py_golden(lib, name):
     return res
 
 
-def run_qpsk(lib, n=200000, seeds=(41, 42), window=(-40000.0, 40000.0)):
+def run_qpsk(lib, n=200000, seeds=(41, 42), window=(-40000.0, 40000.0), fast=False):
     """configs[2]: QPSK record, x^4 carrier estimator (df=freq/4, Doc/07_Demodulation.md:60-63), replica
     (codei+j*codeq)-mean of experiments/220822_qpsk_vs_bpsk/goqpsk.m:10-16, 100 kchip code (17 bits, taps 9/15)."""
     fs = 5e6
     chips = prn.prn_file_bytes(17, n // 2, 9, 15)
     code = oc.code_qpsk(chips)
     recs = [synth.record_pair(code, s, fs=fs, ch1=dict(snr_db=0.0), ch2=dict(snr_db=3.0))[0] for s in seeds]
-    with Correlator(nsamples=n, fs=fs, modulation="qpsk", window_hz=window, max_batch=2, lib=lib) as cor:
+    with Correlator(nsamples=n, fs=fs, modulation="qpsk", window_hz=window, max_batch=2, lib=lib, fast_peak=fast) as cor:
         cor.set_code(chips, qpsk=True)
         res = cor.process(np.stack(recs))
     freq = oc.freq_axis_G(fs, n)

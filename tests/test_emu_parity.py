@@ -45,6 +45,13 @@ def test_fast_peak_path_matches_the_oracle(n):
     pc.run_variant_g(pc.EMU_LIB, n, seeds=(11, 12, 13), fast=True)
 
 
+def test_fast_peak_path_with_fine_frequency_and_qpsk():
+    """The fast peak path behind the other front ends: fine-frequency refinement (golden outputs of the reference's
+    python) and the complex QPSK replica with the x^4 estimator."""
+    pc.run_ref_py_golden(pc.EMU_LIB, "n2e5", fast=True)
+    pc.run_qpsk(pc.EMU_LIB, fast=True)
+
+
 def test_fast_peak_path_falls_back_without_a_peak():
     pc.run_fast_peak_fallback(pc.EMU_LIB, 10000)
 

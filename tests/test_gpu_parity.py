@@ -57,6 +57,13 @@ def test_fast_peak_path_matches_the_oracle(n):
     pc.run_variant_g(pc.CUDA_LIB, n, seeds=(11, 12) if n >= 1000000 else (11, 12, 13), fast=True)
 
 
+def test_fast_peak_path_with_fine_frequency_and_qpsk():
+    """Fast peak path behind the fine-frequency front end (golden outputs of the reference's own python at N = 5e6)
+    and with the complex QPSK replica / x^4 estimator."""
+    pc.run_ref_py_golden(pc.CUDA_LIB, "n5e6", fast=True)
+    pc.run_qpsk(pc.CUDA_LIB, fast=True)
+
+
 def test_fast_peak_path_falls_back_without_a_peak():
     pc.run_fast_peak_fallback(pc.CUDA_LIB, 250000)
 
