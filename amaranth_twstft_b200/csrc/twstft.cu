@@ -437,10 +437,27 @@ int twstft_process_windows(twstft_plan* p, const int16_t* iq, int on_device, siz
         a.d_raw = d_iq; a.nrec = nb; a.nch = p->nch; a.rec_stride = 0; a.d_rec_offset = p->d_off;
         a.estimate = 0; a.d_df_in = p->d_dfin; a.variant = p->cfg.variant; a.ddof = p->cfg.ddof;
         a.fs = p->cfg.fs; a.d_out = p->d_res;
+        a.allow_fast = p->cfg.fast_peak;
         if (p->pipe->correlate(a) != 0) { rc = fail(p, TWSTFT_E_CUDA, p->be.err_string()); break; }
         p->be.d2h(results + w0 * p->nch, p->d_res, sizeof(Result) * nb * p->nch);
         p->be.sync();
         if (!p->be.ok()) rc = fail(p, TWSTFT_E_CUDA, p->be.err_string());
+        // fast peak path: windows whose certificate failed (status bit 2) go through the full path, one at a time
+        for (int i = 0; i < nb && rc == TWSTFT_OK && p->cfg.fast_peak; i++) {
+            bool flagged = false;
+            for (int c = 0; c < p->nch; c++) flagged = flagged || (((int)results[(w0 + i) * p->nch + c].status) & 4);
+            p->fast_records++;
+            if (!flagged) continue;
+            p->fast_rerun++;
+            p->be.h2d(p->d_off, &off[i], sizeof(i64));
+            p->be.h2d(p->d_dfin, df + (w0 + i) * p->nch, sizeof(double) * p->nch);
+            RunArgs b = a;
+            b.nrec = 1; b.allow_fast = 0;
+            if (p->pipe->correlate(b) != 0) { rc = fail(p, TWSTFT_E_CUDA, p->be.err_string()); break; }
+            p->be.d2h(results + (w0 + i) * p->nch, p->d_res, sizeof(Result) * p->nch);
+            p->be.sync();
+            if (!p->be.ok()) rc = fail(p, TWSTFT_E_CUDA, p->be.err_string());
+        }
     }
     if (tmp) { p->be.sync(); p->be.free(tmp); }
     return rc;

@@ -90,7 +90,7 @@ typedef struct twstft_config {
                            the peak decided on the windowed correlation, and `puissance` is sum|fft(y)|^2
                            (main.cpp:295) instead of var(y).  Scales stay Octave's (ifft 1/n): FFTW's unnormalised
                            values are 3N times xval*, and the stored correction1 is indice-1+correction */
-    int fast_peak;      /* 1: twstft_process / twstft_process_device find the interpolated maximum from ONE inverse
+    int fast_peak;      /* 1: twstft_process / twstft_process_device / twstft_process_windows find the interpolated maximum from ONE inverse
                            transform plus exactly evaluated lags around its maximum, guarded by a rigorous bound on
                            every other interpolated sample; records that fail the bound (no correlation peak) are
                            re-run through the full three-transform path, so results are identical (k_fast.cuh).

@@ -142,13 +142,16 @@ def run_qpsk(lib, n=200000, seeds=(41, 42), window=(-40000.0, 40000.0), fast=Fal
             assert_row_matches(res[i, ch - 1], ref[ch], where=f"QPSK seed={seeds[i]} ch{ch}")
 
 
-def run_variant_k(lib, n, delay, df=1234.5, seed=77):
+def run_variant_k(lib, n, delay, df=1234.5, seed=77, fast=False):
     """processing(d,k,df) of claudio_aligned_code_lo_separate.m:24-77 on one single-channel window."""
     bits, code = make_code(n)
     raw, _ = synth.record_single(code, seed, delay=delay, df=df, snr_db=-5.0)
-    with Correlator(nsamples=n, variant="K", layout="single", max_batch=2, lib=lib) as cor:
+    with Correlator(nsamples=n, variant="K", layout="single", max_batch=2, lib=lib, fast_peak=fast) as cor:
         cor.set_code(bits)
         res = cor.process_windows(raw, [0], [df])
+        if fast:
+            at_end = delay < 200 or delay > n - 200          # the evaluated segment would wrap: full path by design
+            assert cor.fast_counters[0] == 1 and (cor.fast_counters[1] == 0 or n < 100000 or at_end), cor.fast_counters
     d = oc.unpack_single(raw)
     ref = oc.processing_K(d - d.mean(), df, oc.fcode_K(code), code)
     assert_row_matches(res[0, 0], ref, where=f"K N={n} delay={delay}")

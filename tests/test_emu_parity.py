@@ -52,6 +52,12 @@ def test_fast_peak_path_with_fine_frequency_and_qpsk():
     pc.run_qpsk(pc.EMU_LIB, fast=True)
 
 
+@pytest.mark.parametrize("delay", [1234.56, 3.2, 199998.7])
+def test_fast_peak_path_variant_k_windows(delay):
+    """processing(d,k,df) of the K scripts through the fast peak path, including peaks at the array ends (fallback)."""
+    pc.run_variant_k(pc.EMU_LIB, 200000, delay, fast=True)
+
+
 def test_fast_peak_path_falls_back_without_a_peak():
     pc.run_fast_peak_fallback(pc.EMU_LIB, 10000)
 

@@ -64,6 +64,11 @@ def test_fast_peak_path_with_fine_frequency_and_qpsk():
     pc.run_qpsk(pc.CUDA_LIB, fast=True)
 
 
+@pytest.mark.parametrize("n,delay", [(200000, 1234.56), (200000, 0.4), (5000000, 2500000.3)])
+def test_fast_peak_path_variant_k_windows(n, delay):
+    pc.run_variant_k(pc.CUDA_LIB, n, delay, fast=True)
+
+
 def test_fast_peak_path_falls_back_without_a_peak():
     pc.run_fast_peak_fallback(pc.CUDA_LIB, 250000)
 
