@@ -53,6 +53,7 @@ struct ColParams {
     u64* part_key;         // [y][ntx]
     double* part_stat;     // COL_INV_ARGMAX_STATS: [y][ntx][2]  sum|z|, sum|z|^2 of the tile
     u64* part_key2;        // COL_INV_ARGMAX_K2: [y][ntx]
+    const int* tile_list;  // COL_INV_ARGMAX_K2, optional: [y][ntx] column tile of work item (x, y) (a few tiles per lane)
 };
 
 // N2C / NCH: row length and channel count as compile-time constants (0 = take them from Params), so that
@@ -104,13 +105,14 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
         const i64 total = (i64)p.ntx * p.ny;
         return bx < total ? (int)((total - bx + gdim - 1) / gdim) : 0;
     }
-    struct Work { int x, y; };
+    struct Work { int x, y, tile; };     // x: slot of the result arrays, tile: column tile (= x unless a tile list is given)
     static HD Work work_of(const Params& p, const Blk& blk, int it)
     {
         const i64 w = (i64)blk.x + (i64)it * blk.gx;
         Work k;
         k.x = (int)(w % p.ntx);
         k.y = (int)(w / p.ntx);
+        k.tile = (MODE == COL_INV_ARGMAX_K2 && p.tile_list) ? p.tile_list[w] : k.x;
         return k;
     }
 
@@ -135,7 +137,7 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
     // with the int16 unpack / mean removal / pre-transform operation fused in
     static HD void load0(const Params& p, const Work& wk, int s, int j, Regs& r)
     {
-        const int col = wk.x * TS + s;
+        const int col = wk.tile * TS + s;
         if (SRC == SRC_RAW) {
             const i64 lane = (i64)wk.y * nchof(p) + col % nchof(p);
             float mx = 0.f, my = 0.f;
@@ -191,7 +193,7 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
 
     static HD void epilogue(const Params& p, const Work& wk, int s, int j, Regs& r, const float2* g)
     {
-        const int col = wk.x * TS + s;
+        const int col = wk.tile * TS + s;
         const int ch = (SRC == SRC_RAW) ? col % nchof(p) : 0;
         const int n2 = (SRC == SRC_RAW) ? col / nchof(p) : col;
         if (MODE == COL_FWD) {
@@ -257,7 +259,7 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
             if (MODE == COL_FWD) {
                 for (int t = tid; t < NG; t += NTA) {
                     const int s2 = t % TS, m = t / TS;
-                    const int col2 = wk.x * TS + s2;
+                    const int col2 = wk.tile * TS + s2;
                     const i64 n2b = (SRC == SRC_RAW) ? col2 / nchof(p) : col2;
                     gtab[m * TS + s2] = cis_cycles(-(double)(n2b * S::NSLAST * m) * p.invN);
                 }
@@ -279,7 +281,7 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
             const unsigned rowlen = (unsigned)p.nq * (unsigned)n2of(p);
             const int row1 = (int)(key_index(r.key) / rowlen);
             const int q = wk.y % p.nq;
-            const int col = wk.x * TS + s;
+            const int col = wk.tile * TS + s;
             u64 best = 0;
             last_stage_visit<S>(j, r.v, [&](int, float2 x, int b, int m) {
                 const int c = S::NTS * b + m * S::NSLAST;

@@ -29,53 +29,78 @@ HD int fast_lag_j(int s) { const int a[4] = {1, 2, 4, 5}; return s < 4 ? a[s] : 
 
 struct FastPrepParams {
     const u64* key1;       // [lane][ntile] tile maxima of the 1x correlation (index = n)
-    const u64* key2;       // [lane][ntile] maxima over the rows other than the row of key1
+    const u64* key2;       // KFastA2: [lane][3] maxima of the three tiles of S over the rows other than their maximum's
     int ntile, tsi;        // tiles per row, columns per tile
     int N2, nrow;          // row length, rows (N = N2 * nrow)
     i64* nstar;            // [lane] 1x arg-max
     i64* base;             // [lane] first sample of S = the three column tiles around n* in linear time (may span two rows)
+    int* tiles;            // [lane][3] column tiles of S (work list of the second-maximum launch)
     double* a2;            // [lane] largest |z| outside S (unnormalised units of the inverse transform)
     int* fail;             // [lane] 1: S would wrap around the array ends -> full path
 };
+// 1x arg-max, the segment S and its three column tiles
 struct KFastPrep {
     typedef FastPrepParams Params;
     static const char* name() { return "fast_prep"; }
     static constexpr bool PERSISTENT = false;
-    static constexpr int NT = 256, MINB = 4, NPH = 3, NSUM = 1;
-    struct Regs { u64 key; u64 kmax; double dsum[NSUM]; };
+    static constexpr int NT = 256, MINB = 4, NPH = 2, NSUM = 1;
+    struct Regs { u64 key; double dsum[NSUM]; };
     static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }
     static HD constexpr int sync_after(int) { return SYNC_MAXKEY; }
     template <int PH> static HD void phase(const Params& p, const Blk& blk, int tid, Regs& r, unsigned char*)
     {
         const i64 lane = blk.y;
         const u64* k1 = p.key1 + lane * p.ntile;
-        const u64* k2 = p.key2 + lane * p.ntile;
         if (PH == 0) {
             u64 best = 0;
             for (int t = tid; t < p.ntile; t += NT) best = k1[t] > best ? k1[t] : best;
             r.key = best;
-        } else if (PH == 1) {
-            r.kmax = r.key;
+        } else if (tid == 0) {
             const i64 ns = (i64)key_index(r.key);
+            const i64 n = (i64)p.N2 * p.nrow;
             const i64 base = (ns / p.tsi) * p.tsi - p.tsi;           // S = [base, base + 3 tsi) in linear time
+            p.nstar[lane] = ns;
+            p.base[lane] = base < 0 ? 0 : base;
+            p.fail[lane] = (base < 0 || base + 3 * (i64)p.tsi > n) ? 1 : 0;   // S would wrap the array
+            for (int c = 0; c < 3; c++) {
+                i64 b = base + (i64)c * p.tsi;
+                b = b < 0 ? 0 : (b >= n ? n - 1 : b);
+                p.tiles[lane * 3 + c] = (int)((b % p.N2) / p.tsi);
+            }
+        }
+    }
+};
+// A2: the largest 1x magnitude outside S -- tile maxima elsewhere; in the three (row, tile) cells of S the maximum
+// over the OTHER rows of that tile (COL_INV_ARGMAX_K2 run on those three tiles only)
+struct KFastA2 {
+    typedef FastPrepParams Params;
+    static const char* name() { return "fast_a2"; }
+    static constexpr bool PERSISTENT = false;
+    static constexpr int NT = 256, MINB = 4, NPH = 2, NSUM = 1;
+    struct Regs { u64 key; double dsum[NSUM]; };
+    static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }
+    static HD constexpr int sync_after(int) { return SYNC_MAXKEY; }
+    template <int PH> static HD void phase(const Params& p, const Blk& blk, int tid, Regs& r, unsigned char*)
+    {
+        const i64 lane = blk.y;
+        const u64* k1 = p.key1 + lane * p.ntile;
+        if (PH == 0) {
+            const i64 ns = p.nstar[lane];
+            const i64 base = (ns / p.tsi) * p.tsi - p.tsi;
             u64 best = 0;
             for (int t = tid; t < p.ntile; t += NT) {
                 u64 k = k1[t];
-                for (int c = 0; c < 3; c++) {                        // the three (row, tile) cells that make up S
+                for (int c = 0; c < 3; c++) {
                     const i64 b = base + (i64)c * p.tsi;
-                    if (b >= 0 && t == (int)((b % p.N2) / p.tsi) && (i64)key_index(k) / p.N2 == b / p.N2) k = k2[t];
+                    if (b >= 0 && t == (int)((b % p.N2) / p.tsi) && (i64)key_index(k) / p.N2 == b / p.N2)
+                        k = p.key2[lane * 3 + c];
                 }
                 const u64 v = (k >> 32) << 32;              // compare magnitudes only
                 best = v > best ? v : best;
             }
             r.key = best;
         } else if (tid == 0) {
-            const i64 ns = (i64)key_index(r.kmax);
-            const i64 base = (ns / p.tsi) * p.tsi - p.tsi;
-            p.nstar[lane] = ns;
-            p.base[lane] = base < 0 ? 0 : base;
             p.a2[lane] = sqrt((double)key_value(r.key));
-            p.fail[lane] = (base < 0 || base + 3 * (i64)p.tsi > (i64)p.N2 * p.nrow) ? 1 : 0;   // S would wrap the array
         }
     }
 };

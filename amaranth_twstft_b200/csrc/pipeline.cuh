@@ -96,7 +96,7 @@ public:
         void* all[] = {d_blob_c, d_blob_r, d_code, d_qconst, d_A, d_B, d_sums, d_energy, d_df, d_peakpart,
                        d_keyrow, d_keycol, d_sbin, d_p0, d_y0, d_lrow, d_lcol, d_stat, d_bankpart, d_ang, d_finepart,
                        d_code_win, d_P, d_R2, d_U2, d_keycol2, d_fn, d_fbase, d_fa2, d_ffail, d_penergy, d_spart,
-                       d_lagpart, d_hbtab, d_fwork};
+                       d_lagpart, d_hbtab, d_fwork, d_ftiles, d_fk1};
         for (void* p : all) be->free(p);
     }
     i64 size() const override { return N; }
@@ -171,7 +171,8 @@ public:
     u64* d_keycol2 = nullptr;
     i64 *d_fn = nullptr, *d_fbase = nullptr;
     double *d_fa2 = nullptr, *d_penergy = nullptr, *d_spart = nullptr, *d_lagpart = nullptr, *d_hbtab = nullptr, *d_fwork = nullptr;
-    int* d_ffail = nullptr;
+    int *d_ffail = nullptr, *d_ftiles = nullptr;
+    u64* d_fk1 = nullptr;
     static double fast_hb(double t, double n)
     {
         const double s = fabs(sin(3.14159265358979323846 * t / n));
@@ -208,7 +209,9 @@ public:
             d_P = dalloc<float2>((size_t)max_lanes * N);
             d_R2 = dalloc<float2>((size_t)max_lanes * N2);
             d_U2 = dalloc<float2>(N2);
-            d_keycol2 = dalloc<u64>((size_t)max_lanes * NCOLTILE_I);
+            d_keycol2 = dalloc<u64>((size_t)max_lanes * 3);
+            d_fk1 = dalloc<u64>((size_t)max_lanes * 3);
+            d_ftiles = dalloc<int>((size_t)max_lanes * 3);
             d_fn = dalloc<i64>(max_lanes);
             d_fbase = dalloc<i64>(max_lanes);
             d_fa2 = dalloc<double>(max_lanes);
@@ -546,13 +549,19 @@ public:
         be->template launch<K1>(dim3((unsigned)g, 1, 1), r);
         ColParams c{};
         c.src = d_B; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.invN = 1.0 / (double)N; c.nch = 1; c.nq = 1;
-        c.part_key = d_keycol; c.part_key2 = d_keycol2; c.ntx = NCOLTILE_I; c.ny = lanes;
-        typedef KCol<CS, TSI, SRC_CF32, COL_INV_ARGMAX_K2, 0, N2, 1> KC2;
-        be->template launch<KC2>(pgrid<KC2>((i64)c.ntx * c.ny), c);
+        c.part_key = d_keycol; c.ntx = NCOLTILE_I; c.ny = lanes;
+        typedef KCol<CS, TSI, SRC_CF32, COL_INV_ARGMAX, 0, N2, 1> KCI;
+        be->template launch<KCI>(pgrid<KCI>((i64)c.ntx * c.ny), c);
         FastPrepParams fp{};
         fp.key1 = d_keycol; fp.key2 = d_keycol2; fp.ntile = NCOLTILE_I; fp.tsi = TSI; fp.N2 = N2; fp.nrow = L1;
-        fp.nstar = d_fn; fp.base = d_fbase; fp.a2 = d_fa2; fp.fail = d_ffail;
+        fp.nstar = d_fn; fp.base = d_fbase; fp.tiles = d_ftiles; fp.a2 = d_fa2; fp.fail = d_ffail;
         be->template launch<KFastPrep>(dim3(1, lanes, 1), fp);
+        // second maxima (rows other than the tile maximum's) of the three column tiles of S only
+        ColParams c2 = c;
+        c2.part_key = d_fk1; c2.part_key2 = d_keycol2; c2.ntx = 3; c2.tile_list = d_ftiles;
+        typedef KCol<CS, TSI, SRC_CF32, COL_INV_ARGMAX_K2, 0, N2, 1> KC2;
+        be->template launch<KC2>(pgrid<KC2>((i64)c2.ntx * c2.ny), c2);
+        be->template launch<KFastA2>(dim3(1, lanes, 1), fp);
         PeakEvalParams pe{};
         pe.part_key = d_keycol; pe.npart = 0; pe.B = d_B; pe.N = N; pe.nq = 1; pe.L1 = L1; pe.N2 = N2;
         pe.p0_out = d_p0; pe.part = d_spart; pe.p0_in = d_fbase; pe.npts_rt = 3 * TSI; pe.dlo_rt = 0;

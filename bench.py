@@ -41,8 +41,8 @@ ALG_BYTES_N = {"mean": 4, "col_fwd_raw": 12, "row_fwd_argmax": 8, "row_corr": 64
 MOVED_BYTES_N = {"mean": 4, "col_fwd_raw": 12, "row_fwd_argmax": 8, "row_corr": 32, "col_inv_argmax": 24}
 # fast peak path (k_fast.cuh, default): one inverse transform; row_corr reads A 8N, writes B 8N and P 8N; the column
 # pass reads 8N and does the job SURVEY budgets at 24N; the exact lags around the maximum read P once more (8N)
-ALG_BYTES_N_FAST = {"mean": 4, "col_fwd_raw": 12, "row_fwd_argmax": 8, "row_corr": 64, "col_inv_argmax_k2": 24}
-MOVED_BYTES_N_FAST = {"mean": 4, "col_fwd_raw": 12, "row_fwd_argmax": 8, "row_corr": 24, "col_inv_argmax_k2": 8,
+ALG_BYTES_N_FAST = {"mean": 4, "col_fwd_raw": 12, "row_fwd_argmax": 8, "row_corr": 64, "col_inv_argmax": 24}
+MOVED_BYTES_N_FAST = {"mean": 4, "col_fwd_raw": 12, "row_fwd_argmax": 8, "row_corr": 24, "col_inv_argmax": 8,
                       "fast_lag_p": 8}
 LAUNCHES_PER_LANE = {"col_fwd_raw": 2}          # estimator pass + derotated pass
 ALG_TOTAL_N = sum(v * LAUNCHES_PER_LANE.get(k, 1) for k, v in MOVED_BYTES_N.items())   # 92
