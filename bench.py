@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 N = 5000000
 FS = 5e6
 CODE = (22, 3, 2500000)          # bitlen, taps, noiselen (experiments/221207_twoway_codes/codes/noiselen2500000_bitlen22_taps03)
-RECORDS_PER_STEP = 16
+RECORDS_PER_STEP = 32
 METRIC = "two-channel 1-s 5 MS/s records correlated per second"
 UNIT = "records/s"
 SURVEY_BYTES_PER_RECORD = 1.4e9  # 140*N bytes per channel, two channels
