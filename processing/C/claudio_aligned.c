@@ -99,6 +99,7 @@ int main(int argc, char** argv)
     cc = ce;
     cc.nsamples = (int64_t)nchips * cc.samples_per_chip; cc.max_batch = batch > 0 ? batch : 32;
     cc.win_lo_hz = -20000; cc.win_hi_hz = 20000;
+    cc.fast_peak = 1;      /* one inverse transform + certificate per window; uncertified windows re-run in full: same rows */
     twstft_plan *est = NULL, *cor = NULL;
     if (twstft_plan_create(&ce, &est) != TWSTFT_OK) return die(est, "twstft_plan_create (block estimator)");
     if (twstft_plan_create(&cc, &cor) != TWSTFT_OK) return die(cor, "twstft_plan_create (correlator)");
