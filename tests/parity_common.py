@@ -255,6 +255,26 @@ def run_fast_peak_fallback(lib, n, seed=31):
     return out
 
 
+def run_fast_peak_degenerate(lib, n=10000):
+    """All-zero, constant and single-impulse records: nothing to certify, every record takes the full path and the
+    rows (NaNs included) are those of a plan without the fast peak path."""
+    bits, _ = make_code(n)
+    zero = np.zeros(4 * n, dtype=np.int16)
+    dc = np.full(4 * n, 1234, dtype=np.int16)
+    imp = np.zeros(4 * n, dtype=np.int16)
+    imp[4 * 777], imp[4 * 777 + 2] = 30000, -30000
+    recs = np.stack([zero, dc, imp])
+    out = {}
+    for fast in (False, True):
+        with Correlator(nsamples=n, max_batch=2, lib=lib, fast_peak=fast) as cor:
+            cor.set_code(bits)
+            out[fast] = cor.process(recs)
+            if fast:
+                assert cor.fast_counters[0] == 3 and cor.fast_counters[1] >= 2, cor.fast_counters
+    for name in out[False].dtype.names:
+        assert np.array_equal(out[False][name], out[True][name], equal_nan=True), name
+
+
 def run_doppler_bank(lib, n=10000, nbins=16, span=2000.0, true_df=437.0, seed=3, snr_db=-10.0, check_every=1):
     """configs[3]: one record correlated over a bank of Doppler bins (the per-bin body of search_df,
     claudio_aligned_code_re_separate.m:33-42): peak index bit-exact, magnitude and metric to 1e-4."""

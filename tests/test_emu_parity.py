@@ -58,6 +58,10 @@ def test_fast_peak_path_variant_k_windows(delay):
     pc.run_variant_k(pc.EMU_LIB, 200000, delay, fast=True)
 
 
+def test_fast_peak_path_degenerate_records():
+    pc.run_fast_peak_degenerate(pc.EMU_LIB)
+
+
 def test_fast_peak_path_falls_back_without_a_peak():
     pc.run_fast_peak_fallback(pc.EMU_LIB, 10000)
 

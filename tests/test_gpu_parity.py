@@ -69,6 +69,10 @@ def test_fast_peak_path_variant_k_windows(n, delay):
     pc.run_variant_k(pc.CUDA_LIB, n, delay, fast=True)
 
 
+def test_fast_peak_path_degenerate_records():
+    pc.run_fast_peak_degenerate(pc.CUDA_LIB, 250000)
+
+
 def test_fast_peak_path_falls_back_without_a_peak():
     pc.run_fast_peak_fallback(pc.CUDA_LIB, 250000)
 
