@@ -21,7 +21,7 @@ typedef long long i64;
 
 struct Blk { int x, y, z, gx; };   // block index and gridDim.x
 
-enum SyncKind { SYNC_BARRIER = 0, SYNC_MAXKEY = 1, SYNC_SUMD = 2, SYNC_MAXKEY_SUMD = 3 };
+enum SyncKind { SYNC_BARRIER = 0, SYNC_MAXKEY = 1, SYNC_SUMD = 2, SYNC_MAXKEY_SUMD = 3, SYNC_SUMF16 = 4 };
 
 // ------------------------------------------------------------------ complex fp32 helpers
 // On sm_100a a complex value lives in an aligned 64-bit register pair and the arithmetic uses the
@@ -148,32 +148,6 @@ HD double2 cis_cycles_d(double c)
 }
 
 HD double2 dmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-
-// Asynchronous global->shared copies (LDGSTS).  On the host (test emulation) they complete at once.
-HD void cp_async8(void* smem_dst, const void* gsrc)
-{
-#ifdef __CUDA_ARCH__
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc) : "memory");
-#else
-    *reinterpret_cast<float2*>(smem_dst) = *reinterpret_cast<const float2*>(gsrc);
-#endif
-}
-HD void cp_async4(void* smem_dst, const void* gsrc)
-{
-#ifdef __CUDA_ARCH__
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc) : "memory");
-#else
-    *reinterpret_cast<int*>(smem_dst) = *reinterpret_cast<const int*>(gsrc);
-#endif
-}
-HD void cp_async_wait_all()
-{
-#ifdef __CUDA_ARCH__
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-#endif
-}
 
 // Pull one 128-byte line towards L2 ahead of the loads of the next work item (no-op on the host).
 HD void prefetch_l2(const void* g)

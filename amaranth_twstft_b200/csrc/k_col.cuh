@@ -121,9 +121,9 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
     static constexpr bool USE_LROW = (OP == 1 || SPLIT == 2);
     static HD float2 power_op(float2 x)
     {
-        if (POW >= 2) {
-            x = make_float2(x.x * x.x - x.y * x.y, 2.f * x.x * x.y);
-            if (POW == 4) x = make_float2(x.x * x.x - x.y * x.y, 2.f * x.x * x.y);
+        if (POW >= 2) {       // x*x as one packed complex multiply (two instructions instead of four scalar ones)
+            x = cmul(x, x);
+            if (POW == 4) x = cmul(x, x);
         }
         return x;
     }

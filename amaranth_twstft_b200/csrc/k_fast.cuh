@@ -145,48 +145,74 @@ struct KLagP {
     typedef LagPParams Params;
     static const char* name() { return "fast_lag_p"; }
     static constexpr bool PERSISTENT = false;
-    static constexpr int NT = 256, MINB = 4, NPH = 2, NSUM = 2 * FAST_NLAG;
-    struct Regs { u64 key; double dsum[NSUM]; };
+    static constexpr int NT = 256, MINB = 3, NPH = 2, NSUM = 1;
+    static_assert(2 * FAST_NLAG == 16, "the sixteen partial sums go through SYNC_SUMF16");
+    struct Regs { u64 key; double dsum[NSUM]; float fsum[16]; };
     static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }
-    static HD constexpr int sync_after(int) { return SYNC_SUMD; }
+    static HD constexpr int sync_after(int) { return SYNC_SUMF16; }
+    // one spectrum sample: a = P*R2, then a*w^j and a*conj(w^j) for j = 1, 2, 4, 5 share their products: with
+    // w^j = c + i s,  a w = a c + i (a s),  a conj(w) = a c - i (a s); accumulate Sr = sum a c and Ss = sum a s (one
+    // packed FMA each) and combine once at the end
+    static HD void accumulate(float2 pv, float2 r2, float2 u, float2* sr, float2* ss)
+    {
+        const float2 a = cmul(pv, r2);
+        float2 w[4];
+        w[0] = u;
+        w[1] = cmul(w[0], w[0]);
+        w[2] = cmul(w[1], w[1]);
+        w[3] = cmul(w[2], w[0]);
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            sr[s] = caxpy(w[s].x, a, sr[s]);
+            ss[s] = caxpy(w[s].y, a, ss[s]);
+        }
+    }
     template <int PH> static HD void phase(const Params& p, const Blk& blk, int tid, Regs& r, unsigned char*)
     {
         const i64 lane = blk.y;
         const int k1 = blk.x;
         if (PH == 0) {
-            // a*w^j and a*conj(w^j) share their products: with w^j = c + i s,  a w = a c + i (a s),  a conj(w) = a c - i (a s);
-            // accumulate Sr = sum a c and Ss = sum a s (one packed FMA each) and combine once at the end
             float2 sr[4], ss[4];
 #pragma unroll
             for (int s = 0; s < 4; s++) sr[s] = ss[s] = make_float2(0.f, 0.f);
-            const float2* row = p.P + (lane * p.L1 + k1) * (i64)p.N2;
-            const float2* r2 = p.R2 + lane * p.N2;
-#pragma unroll 4
-            for (int k2 = tid; k2 < p.N2; k2 += NT) {
-                const float2 a = cmul(row[k2], r2[k2]);
-                float2 w[4];
-                w[0] = p.U2[k2];
-                w[1] = cmul(w[0], w[0]);
-                w[2] = cmul(w[1], w[1]);
-                w[3] = cmul(w[2], w[0]);
+            // two spectrum samples per 16-byte load, four loads of each stream in flight per thread: the row of P
+            // comes from HBM exactly once, the two tables (64 KB each) stay in L1/L2
+            const float4* row = reinterpret_cast<const float4*>(p.P + (lane * p.L1 + k1) * (i64)p.N2);
+            const float4* r2 = reinterpret_cast<const float4*>(p.R2 + lane * p.N2);
+            const float4* u2 = reinterpret_cast<const float4*>(p.U2);
+            const int npair = p.N2 / 2;
+            constexpr int U = 4;
+            int i = tid;
+            for (; i + (U - 1) * NT < npair; i += U * NT) {
+                float4 a[U], b[U], c[U];
 #pragma unroll
-                for (int s = 0; s < 4; s++) {
-                    sr[s] = caxpy(w[s].x, a, sr[s]);
-                    ss[s] = caxpy(w[s].y, a, ss[s]);
+                for (int u = 0; u < U; u++) a[u] = row[i + u * NT];
+#pragma unroll
+                for (int u = 0; u < U; u++) { b[u] = r2[i + u * NT]; c[u] = u2[i + u * NT]; }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    accumulate(make_float2(a[u].x, a[u].y), make_float2(b[u].x, b[u].y), make_float2(c[u].x, c[u].y), sr, ss);
+                    accumulate(make_float2(a[u].z, a[u].w), make_float2(b[u].z, b[u].w), make_float2(c[u].z, c[u].w), sr, ss);
                 }
             }
-            float2 acc[FAST_NLAG];
-#pragma unroll
-            for (int s = 0; s < 4; s++) {
-                acc[s] = cadd(sr[s], rot_pi(ss[s]));
-                acc[s + 4] = csub(sr[s], rot_pi(ss[s]));
+            for (; i < npair; i += NT) {
+                const float4 a = row[i], b = r2[i], c = u2[i];
+                accumulate(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y), sr, ss);
+                accumulate(make_float2(a.z, a.w), make_float2(b.z, b.w), make_float2(c.z, c.w), sr, ss);
+            }
+            if ((p.N2 & 1) && tid == 0) {            // odd row length: the last sample alone
+                const int k2 = p.N2 - 1;
+                accumulate(p.P[(lane * p.L1 + k1) * (i64)p.N2 + k2], p.R2[lane * p.N2 + k2], p.U2[k2], sr, ss);
             }
 #pragma unroll
-            for (int s = 0; s < FAST_NLAG; s++) { r.dsum[2 * s] = (double)acc[s].x; r.dsum[2 * s + 1] = (double)acc[s].y; }
-        } else if (tid == 0) {
+            for (int s = 0; s < 4; s++) {
+                const float2 lo = cadd(sr[s], rot_pi(ss[s])), hi = csub(sr[s], rot_pi(ss[s]));
+                r.fsum[2 * s] = lo.x; r.fsum[2 * s + 1] = lo.y;
+                r.fsum[2 * (s + 4)] = hi.x; r.fsum[2 * (s + 4) + 1] = hi.y;
+            }
+        } else if (tid < 2 * FAST_NLAG) {
             // raw row sums; the row factor R1[k1] u1[k1]^j is applied by the reduction in KFastCert (one thread per row)
-            double* o = p.part + (lane * p.L1 + k1) * (2 * FAST_NLAG);
-            for (int i = 0; i < 2 * FAST_NLAG; i++) o[i] = r.dsum[i];
+            p.part[(lane * p.L1 + k1) * (2 * FAST_NLAG) + tid] = r.dsum[0];
         }
     }
 };

@@ -62,6 +62,18 @@ template <int E> __device__ __forceinline__ void tmem_fetch(unsigned base, float
 }
 #endif
 
+// chunk c (8 columns = 4 complex values) of this thread's TMEM window
+#if defined(__CUDA_ARCH__)
+template <int NCOL> __device__ __forceinline__ void tmem_fetch4(unsigned base, int c, float2* v4)
+{
+    unsigned w[8];
+    tmem_ld8(tmem_window<NCOL>(base) + 8 * c, w);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 4; i++) v4[i] = make_float2(__uint_as_float(w[2 * i]), __uint_as_float(w[2 * i + 1]));
+}
+#endif
+
 constexpr int tmem_pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
 struct RowCorrParams {
@@ -82,9 +94,21 @@ struct RowCorrParams {
     double* part_penergy;    // with pdst: [lane][nblk] sum |P|^2
 };
 
+#ifndef TWSTFT_CODE_TMEM
+#define TWSTFT_CODE_TMEM 1
+#endif
+#ifndef TWSTFT_CODE_AHEAD
+#define TWSTFT_CODE_AHEAD 0     /* 1: read-only code loads issued one chunk ahead of their use (no gain measured, more spills) */
+#endif
+
 template <class S, int RPC, int NQ> struct KRowCorr {
     typedef RowCorrParams Params;
     static const char* name() { return "row_corr"; }
+    // The 1x kernel (fast peak path, Doppler bank) has no spectrum to park, so tensor memory holds this thread's
+    // share of the CODE row instead: a CTA walks a contiguous run of (row, lane) items, i.e. the same row for many
+    // lanes in a row, and re-reads the code from global memory only when the row changes.  (With the code fetched
+    // per item the 20 dependent L2 round trips of the product loop were a third of all stall samples, ncu r01 g.)
+    static constexpr bool CODE_TMEM = (NQ == 1) && (TWSTFT_CODE_TMEM != 0);
     static_assert(S::NSTAGE >= 2, "row transforms have at least two stages");
     static_assert(S::R0 == S::RLAST && S::SP0 == S::NSLAST, "forward outputs must be the inverse stage-0 operands");
     static_assert(S::R0 % 2 == 0, "negative-frequency split needs an even first radix");
@@ -115,8 +139,9 @@ template <class S, int RPC, int NQ> struct KRowCorr {
         double dsum[NSUM];
         unsigned tmem;       // TMEM base address of this CTA (device)
         float2 obase[(S::L / S::RLAST) / S::NTS];   // four-step twiddle base of this thread's outputs, per item
+        int crow;            // CODE_TMEM: row whose code values sit in this thread's TMEM window (-1: none)
 #ifdef TWSTFT_EMU
-        float2 P[S::E];      // host emulation: the parked spectrum
+        float2 P[S::E];      // host emulation: the parked spectrum / code row
 #endif
     };
     static HD constexpr size_t smem_bytes()
@@ -129,12 +154,17 @@ template <class S, int RPC, int NQ> struct KRowCorr {
     static HD int niter(const Params& p, int bx, int gdim)
     {
         const i64 total = (i64)p.nblk * p.nlanes;
+        if (CODE_TMEM) {     // contiguous run of items per CTA
+            const i64 per = (total + gdim - 1) / gdim, start = (i64)bx * per;
+            return start < total ? (int)(total - start < per ? total - start : per) : 0;
+        }
         return bx < total ? (int)((total - bx + gdim - 1) / gdim) : 0;
     }
     struct Work { int rowblk; i64 lane; };
     static HD Work work_of(const Params& p, const Blk& blk, int it)
     {
-        const i64 w = (i64)blk.x + (i64)it * blk.gx;
+        const i64 total = (i64)p.nblk * p.nlanes;
+        const i64 w = CODE_TMEM ? (i64)blk.x * ((total + blk.gx - 1) / blk.gx) + it : (i64)blk.x + (i64)it * blk.gx;
         Work k;
         k.rowblk = (int)(w / p.nlanes);
         k.lane = w % p.nlanes;
@@ -155,6 +185,24 @@ template <class S, int RPC, int NQ> struct KRowCorr {
         tmem_fetch<S::E>(r.tmem, r.v);
 #elif defined(TWSTFT_EMU)
         for (int i = 0; i < S::E; i++) r.v[i] = r.P[i];
+#endif
+    }
+
+    // four code values (elements 4c .. 4c+3 of this thread) out of tensor memory; warp-collective on the device
+    static HD void code4(const Regs& r, int c, float2* cc)
+    {
+#if defined(__CUDA_ARCH__)
+        tmem_fetch4<2 * S::E>(r.tmem, c, cc);
+#elif defined(TWSTFT_EMU)
+        for (int i = 0; i < 4; i++) cc[i] = r.P[4 * c + i];
+#endif
+    }
+    static HD float2 ldg_ro(const float2* g)
+    {
+#if defined(__CUDA_ARCH__)
+        return __ldg(g);
+#else
+        return *g;
 #endif
     }
 
@@ -181,6 +229,20 @@ template <class S, int RPC, int NQ> struct KRowCorr {
             r.key = 0;
             r.dsum[0] = 0.0;
             if (PSTORE) r.dsum[NSUM - 1] = 0.0;
+            if (CODE_TMEM) {
+                if (it == 0) r.crow = -1;
+                if (r.crow != row) {                      // uniform over the CTA's rows: every thread of a warp takes part
+                    if (active) {
+                        const float2* c = p.code + (i64)row * S::L + j;
+#pragma unroll
+                        for (int b = 0; b < NB0; b++)
+#pragma unroll
+                            for (int m = 0; m < S::R0; m++) r.v[b * S::R0 + m] = ldg_ro(c + S::NTS * b + m * S::SP0);
+                    }
+                    park(r);
+                    r.crow = row;
+                }
+            }
             if (active) {
                 for (int t = tid; t < NG; t += NTA) {      // conjugate four-step twiddle steps of this item's rows
                     const int rl2 = t / S::RLAST, m = t % S::RLAST;
@@ -203,7 +265,7 @@ template <class S, int RPC, int NQ> struct KRowCorr {
             constexpr int NLINE = (int)((size_t)RPC * S::L * sizeof(float2) / 128);
             for (int l = tid; l < NLINE; l += NT) {
                 prefetch_l2(a + (size_t)l * 128);
-                prefetch_l2(c + (size_t)l * 128);
+                if (!CODE_TMEM) prefetch_l2(c + (size_t)l * 128);
             }
         }
         if (F > 0 && ST == 0) {
@@ -232,25 +294,63 @@ template <class S, int RPC, int NQ> struct KRowCorr {
             }
         }
         if (NST == 3 && ST == 1 && active) dif_stage_mid<S>(j, r.v, sm, acc);
-        if (ST == NST - 1) {
+        if (ST == NST - 1 && F == 0) {
+            // forward last stage, then the code product four outputs at a time: the code values come out of tensor
+            // memory (CODE_TMEM) or from read-only loads issued a chunk ahead of their use
+            static_assert(S::E % 4 == 0, "code product walks the outputs in chunks of four");
             if (active) {
                 dif_stage_last<S>(j, r.v, acc);
-                if (F == 0) {
-                    float e = 0.f, e2 = 0.f;
-                    const int cm = p.conj_mode;
-                    float2* pd = (PSTORE && p.pdst) ? p.pdst + wk.lane * p.N + (i64)row * S::L : nullptr;
-                    const float2* c = p.code + (i64)row * S::L;
-                    if (row == 0 && j == 0) p.y0[wk.lane] = r.v[0];
-                    last_stage_visit<S>(j, r.v, [&](int o, float2 x, int b, int m) {
-                        const float2 cc = c[o];
+                if (row == 0 && j == 0) p.y0[wk.lane] = r.v[0];
+            }
+            float e = 0.f, e2 = 0.f;
+            const int cm = p.conj_mode;
+            float2* pd = (PSTORE && p.pdst) ? p.pdst + wk.lane * p.N + (i64)row * S::L : nullptr;
+            const float2* c = p.code + (i64)row * S::L;
+            auto out_index = [&](int el) { return j + S::NTS * (el / S::RLAST) + (el % S::RLAST) * S::NSLAST; };
+            constexpr bool AHEAD = TWSTFT_CODE_AHEAD != 0;
+            float2 cn[4];
+            if (!CODE_TMEM && AHEAD && active) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) cn[i] = ldg_ro(c + out_index(i));
+            }
+#pragma unroll
+            for (int c4 = 0; c4 < S::E / 4; c4++) {
+                float2 cc[4];
+                if (CODE_TMEM) {
+                    code4(r, c4, cc);
+                } else if (AHEAD) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) cc[i] = cn[i];
+                    if (active && c4 + 1 < S::E / 4) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) cn[i] = ldg_ro(c + out_index(4 * (c4 + 1) + i));
+                    }
+                } else if (active) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) cc[i] = ldg_ro(c + out_index(4 * c4 + i));
+                }
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int el = 4 * c4 + i;
+                        const float2 x = r.v[el];
                         e += cnorm(x);
-                        const float2 pr = cm ? cmul(cconj(x), cc) : cmulc(x, cc);
-                        r.v[b * S::R0 + m] = pr;
-                        if (PSTORE && pd) { pd[o] = pr; e2 += cnorm(pr); }
-                    });
-                    r.dsum[0] = (double)e;
-                    if (PSTORE) r.dsum[NSUM - 1] = (double)e2;
-                } else {
+                        const float2 pr = cm ? cmul(cconj(x), cc[i]) : cmulc(x, cc[i]);
+                        r.v[el] = pr;
+                        if (PSTORE && pd) { pd[out_index(el)] = pr; e2 += cnorm(pr); }
+                    }
+                }
+            }
+            if (active) {
+                r.dsum[0] = (double)e;
+                if (PSTORE) r.dsum[NSUM - 1] = (double)e2;
+            }
+            if (NQ > 1) park(r);                          // P -> tensor memory for the polyphases q >= 1
+        }
+        if (ST == NST - 1 && F > 0) {
+            if (active) {
+                dif_stage_last<S>(j, r.v, acc);
+                {
                     constexpr int q = F - 1;
                     float2* d = p.dst + (wk.lane * NQ + q) * p.N + (i64)row * S::L;
                     const float2* gr = gtab + rl * S::RLAST;
@@ -264,7 +364,6 @@ template <class S, int RPC, int NQ> struct KRowCorr {
                     });
                 }
             }
-            if (F == 0 && NQ > 1) park(r);                // P -> tensor memory for the polyphases q >= 1
         }
     }
 };

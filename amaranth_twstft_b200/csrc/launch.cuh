@@ -4,6 +4,8 @@
 //   K::smem_bytes(), template<int PH> K::phase(p, blk, tid, regs, smem), K::sync_after(ph)
 // SYNC_MAXKEY  : regs.key   <- max over the CTA (valid in every thread afterwards)
 // SYNC_SUMD    : regs.dsum[i] <- sum over the CTA for i < K::NSUM (valid in thread 0)
+// SYNC_SUMF16  : regs.dsum[0] of thread i < 16 <- sum over the CTA of regs.fsum[i] (fp32 inside a warp, fp64 across
+//                the warps): 16 shuffles per thread instead of the 160 of sixteen fp64 sums
 #pragma once
 #include "common.cuh"
 
@@ -57,6 +59,39 @@ template <class K> __device__ __forceinline__ void block_sum_d(typename K::Regs&
     }
 }
 
+// Sixteen fp32 sums per thread: transposing butterfly (each exchange halves the number of values a lane carries, so
+// the whole warp reduction is 8+4+2+1+1 shuffles), lanes 2k and 2k+1 end with the warp total of value k; the warp
+// totals are added in fp64 by threads 0..15.
+template <class K> __device__ __forceinline__ void block_sum_f16(typename K::Regs& r, unsigned char* scratch)
+{
+    static_assert(16 * 32 * 8 <= RED_SCRATCH_BYTES, "reduction scratch too small");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NW = (K::NT + 31) / 32;
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = r.fsum[i];
+#pragma unroll
+    for (int h = 8; h >= 1; h >>= 1) {                // offsets 16, 8, 4, 2 keep h values each
+        const bool up = (lane & (2 * h)) != 0;
+#pragma unroll
+        for (int i = 0; i < h; i++) {
+            const float send = up ? v[i] : v[i + h];
+            const float keep = up ? v[i + h] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * h);
+        }
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    double* s = reinterpret_cast<double*>(scratch);
+    __syncthreads();
+    if ((lane & 1) == 0) s[(lane >> 1) * 32 + warp] = (double)v[0];
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        double t = 0.0;
+        for (int w = 0; w < NW; w++) t += s[threadIdx.x * 32 + w];
+        r.dsum[0] = t;
+    }
+}
+
 // Persistent kernels (K::PERSISTENT) loop over work items: phase<PH>(..., it, nit) is run for
 // it = 0..nit-1 with nit = K::niter(p, blockIdx.x, gridDim.x).
 template <class K, int PH>
@@ -71,6 +106,7 @@ __device__ __forceinline__ void run_phases(const typename K::Params& p, const Bl
         if constexpr (kind == SYNC_BARRIER) __syncthreads();
         if constexpr (kind == SYNC_MAXKEY || kind == SYNC_MAXKEY_SUMD) block_max_key<K>(r, scratch);
         if constexpr (kind == SYNC_SUMD || kind == SYNC_MAXKEY_SUMD) block_sum_d<K>(r, scratch);
+        if constexpr (kind == SYNC_SUMF16) block_sum_f16<K>(r, scratch);
         run_phases<K, PH + 1>(p, b, tid, r, smem, it, nit);
     }
 }

@@ -611,11 +611,16 @@ inline IPipe* make_pipe(i64 n)
     typedef FFTSpec<20, 20, 20> R8000;
     typedef FFTSpec<20, 20> R400;
     switch (n) {
-    case 5000000: return new Pipe<FFTSpec<25, 25>, R8000, 1, 16, 8>();    // 1-s window, 2.5 Mchip/s code
+#ifndef TWSTFT_TS_FWD
+#define TWSTFT_TS_FWD 16
+#endif
+    case 5000000: return new Pipe<FFTSpec<25, 25>, R8000, 1, TWSTFT_TS_FWD, 8>();    // 1-s window, 2.5 Mchip/s code
+#ifndef TWSTFT_ONLY_5E6   /* kernel-variant builds of tools/kbench compile the 1-s window only */
     case 1000000: return new Pipe<FFTSpec<5, 25>, R8000, 1, 16>();     // 500 kchip codes
     case 200000: return new Pipe<FFTSpec<25>, R8000, 1, 64>();         // 100 kchip/s code windows
     case 250000: return new Pipe<FFTSpec<25, 25>, R400, 5, 16>();      // test size (same column kernel as 5e6)
     case 10000: return new Pipe<FFTSpec<25>, R400, 5, 16>();           // 5 kchip codes / test size
+#endif
     default: return nullptr;
     }
 }

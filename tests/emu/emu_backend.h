@@ -31,6 +31,14 @@ template <class K, int PH> struct EmuPhases {
                     regs[0].dsum[i] = t;
                 }
             }
+            if constexpr (kind == SYNC_SUMF16) {
+                double t[16];
+                for (int i = 0; i < 16; i++) {
+                    t[i] = 0.0;
+                    for (int tid = 0; tid < K::NT; tid++) t[i] += (double)regs[tid].fsum[i];
+                }
+                for (int i = 0; i < 16; i++) regs[i].dsum[0] = t[i];
+            }
             EmuPhases<K, PH + 1>::run(p, b, regs, smem, it, nit);
         }
     }
