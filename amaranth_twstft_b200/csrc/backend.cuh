@@ -28,9 +28,13 @@ struct Backend {
     cudaError_t err = cudaSuccess;
     long launches = 0;
 
-    bool ok() const { return err == cudaSuccess; }
+    // `err` keeps the first CUDA error of the plan (kernel faults and the like: the context is gone, the plan is
+    // dead).  A failed allocation is NOT such an error: it is remembered in `oom` for the current ABI call only
+    // (use() clears it), so an oversized request returns TWSTFT_E_NOMEM and the plan stays usable.
+    bool oom = false;
+    bool ok() const { return err == cudaSuccess && !oom; }
     void note(cudaError_t e) { if (e != cudaSuccess && err == cudaSuccess) err = e; }
-    const char* err_string() const { return cudaGetErrorString(err); }
+    const char* err_string() const { return (oom && err == cudaSuccess) ? "out of device memory" : cudaGetErrorString(err); }
 
     int init(int dev)
     {
@@ -56,11 +60,17 @@ struct Backend {
         }
         stream = copy_stream = nullptr;
     }
-    void use() { cudaSetDevice(device); }
+    void use() { cudaSetDevice(device); oom = false; }
     void* alloc(size_t bytes)
     {
         void* p = nullptr;
-        note(cudaMalloc(&p, bytes ? bytes : 1));
+        const cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+        if (e == cudaErrorMemoryAllocation) {
+            oom = true;
+            cudaGetLastError();      // clear the (non-sticky) runtime error state
+            return nullptr;
+        }
+        note(e);
         return p;
     }
     void free(void* p) { if (p) cudaFree(p); }

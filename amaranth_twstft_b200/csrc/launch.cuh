@@ -83,11 +83,11 @@ template <class K> __device__ __forceinline__ void block_sum_f16(typename K::Reg
     v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
     double* s = reinterpret_cast<double*>(scratch);
     __syncthreads();
-    if ((lane & 1) == 0) s[(lane >> 1) * 32 + warp] = (double)v[0];
+    if ((lane & 1) == 0) s[warp * 16 + (lane >> 1)] = (double)v[0];
     __syncthreads();
     if (threadIdx.x < 16) {
         double t = 0.0;
-        for (int w = 0; w < NW; w++) t += s[threadIdx.x * 32 + w];
+        for (int w = 0; w < NW; w++) t += s[w * 16 + threadIdx.x];
         r.dsum[0] = t;
     }
 }

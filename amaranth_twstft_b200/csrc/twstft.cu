@@ -176,8 +176,8 @@ static int ensure_bits(twstft_plan* p, size_t n)
     if (p->bits_cap >= n) return 0;
     p->be.free(p->d_bits);
     p->d_bits = (unsigned char*)p->be.alloc(n);
-    p->bits_cap = n;
-    return p->be.ok() ? 0 : -1;
+    p->bits_cap = p->d_bits ? n : 0;
+    return (p->d_bits && p->be.ok()) ? 0 : -1;
 }
 
 static int install_code(twstft_plan* p, const unsigned char* host_bits, size_t nbytes, int qpsk)
@@ -288,7 +288,7 @@ static int ensure_raw(twstft_plan* p)
 {
     if (p->d_raw) return 0;
     p->d_raw = (short2*)p->be.alloc(sizeof(short2) * p->raw_elems_per_rec * p->cfg.max_batch * 2);
-    return p->be.ok() ? 0 : -1;
+    return (p->d_raw && p->be.ok()) ? 0 : -1;
 }
 
 // Fast peak path (k_fast.cuh): rows whose certificate failed carry status bit 2; those records go through the full
@@ -361,8 +361,8 @@ static int ensure_results(twstft_plan* p, size_t rows)
     p->be.sync();
     p->be.free(p->d_res);
     p->d_res = (Result*)p->be.alloc(sizeof(Result) * rows);
-    p->res_cap = rows;
-    return p->be.ok() ? 0 : -1;
+    p->res_cap = p->d_res ? rows : 0;
+    return (p->d_res && p->be.ok()) ? 0 : -1;
 }
 
 // Host records: the input is streamed in chunks through two staging slots so that the PCIe copy of

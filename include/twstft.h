@@ -108,7 +108,9 @@ typedef struct twstft_result {
     double df;            /* carrier offset used for the derotation, Hz */
     double puissance, puissancecode, puissancenoise;
     double carrier_bin;   /* 0-based index of the estimator maximum on the fftshift'ed axis, -1 if df was given */
-    double status;        /* bit0: peak at the array edge (Octave would fail), bit1: fp64 refinement moved the peak */
+    double status;        /* bit0: peak at the array edge (Octave would fail), bit1: fp64 refinement moved the peak,
+                             bit2: fast peak path could not certify the maximum (only ever visible inside the library:
+                             twstft_process* re-run such records through the full path before returning) */
 } twstft_result;
 
 void twstft_default_config(twstft_config* cfg);

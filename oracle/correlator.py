@@ -191,7 +191,9 @@ def df_CPP(raw_file, nch_total, fs=FS, dec=25, foffset=0.0, remote=0):
     idx = idx[idx < ninst]
     t = np.arange(len(idx)) * (dec / fs)
     lo = np.exp(-1j * 2 * np.pi * foffset * t)
-    x1 = (r[4 * idx] + 1j * r[4 * idx + 1]) * lo
+    d1 = r[4 * idx] + 1j * r[4 * idx + 1]
+    m1 = np.mean(d1)                                                    # _mean1 accumulates the RAW samples (:387)
+    x1 = d1 * lo
     L = len(x1)
     freq = np.linspace(-fs / 2 / dec, fs / 2 / dec, L)
     frange = 8000.0
@@ -206,7 +208,7 @@ def df_CPP(raw_file, nch_total, fs=FS, dec=25, foffset=0.0, remote=0):
         kmax = int(w[-1]) if len(w) else 0
         w = np.nonzero(freq <= -2 * frange)[0]
         kmin = int(w[-1]) if len(w) else 0
-    x1 = x1 - np.mean(x1)
+    x1 = x1 - m1                                                        # ... and is subtracted AFTER the derotation (:417-420)
     out = np.fft.fftshift(np.abs(_fft.fft(x1 * x1))) if L % 2 == 0 else None
     if out is None:                                                     # memcpy halves of :413-414 for odd L
         f = np.abs(_fft.fft(x1 * x1))
@@ -215,8 +217,8 @@ def df_CPP(raw_file, nch_total, fs=FS, dec=25, foffset=0.0, remote=0):
     pos1 = int(np.argmax(out[kmin:kmax])) + kmin
     res = {1: freq[pos1] / 2.0 + foffset, "pos1": pos1}
     if remote == 0:
-        x2 = (r[4 * idx + 2] + 1j * r[4 * idx + 3]) * lo
-        x2 = x2 - np.mean(x2)
+        d2 = r[4 * idx + 2] + 1j * r[4 * idx + 3]
+        x2 = d2 * lo - np.mean(d2)                                      # _mean2: raw mean, :392,437-440
         f = np.abs(_fft.fft(x2 * x2))
         h = L // 2
         out2 = np.concatenate([f[h:h + h], f[:h], np.zeros(L - 2 * h)])

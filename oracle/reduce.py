@@ -105,7 +105,9 @@ def gofinal_rows(local, remote, end_epoch, ltfb, local_c=False, remote_c=False, 
     """Rows (epoch, 9 values) written by gofinal_op.m:70-78 (every record) / gofinal_ltfb.m:84-90 (selected)."""
     lo, re = _station(local, local_c, True), _station(remote, remote_c, False)
     n = len(lo["sol1"])
-    dateini = end_epoch - n
+    # gofinal_ltfb.m:48 counts the LOCAL file's records; gofinal_op.m:36-37 evaluates length(indice1) while the
+    # REMOTE file is the one loaded
+    dateini = end_epoch - (n if ltfb else len(re["sol1"]))
     ind = np.nonzero(lo["snr1"] > lo["snr1"].max() - 10)[0]
     res = (lo["sol1"][ind] - lo["sol2"][ind]) / fs / 3
     x = np.arange(1, len(res) + 1, dtype=float)

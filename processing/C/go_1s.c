@@ -203,7 +203,13 @@ int main(int argc, char** argv)
 
     char outname[4096];
     if (argc > 6 && argv[6][0]) snprintf(outname, sizeof outname, "%s", argv[6]);
-    else snprintf(outname, sizeof outname, "%.15g.1s", mjd);       /* [num2str(ladate(p)),'.1s'] */
+    else {   /* [num2str(ladate(p)),'.1s']: num2str of a non-integer prints max(floor(log10(|x|))+5, 5) significant digits */
+        int digits = (mjd != 0.0) ? (int)floor(log10(fabs(mjd))) + 5 : 5;
+        if (digits < 5) digits = 5;
+        if (digits > 16) digits = 16;
+        if (mjd == floor(mjd)) snprintf(outname, sizeof outname, "%.0f.1s", mjd);
+        else snprintf(outname, sizeof outname, "%.*g.1s", digits, mjd);
+    }
     FILE* fo = fopen(outname, "w");
     if (!fo) { fprintf(stderr, "cannot write %s\n", outname); return 1; }
     fprintf(fo, "# MJD\t\tOPlocal\tOPremote\tLTFBlocal\tLTBBremote\n");   /* :253 */

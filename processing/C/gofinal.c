@@ -81,11 +81,16 @@ static const double* need(const mat5_file* mf, const char* a, const char* b, siz
     if (*n == 0 || v->n < *n) *n = v->n;
     return v->re;
 }
-static void load_station(const char* path, int two, station* s)
+static void load_station(const char* path, int two, int ltfb, station* s)
 {
     mat5_file mf;
     if (mat5_load(path, &mf) != 0) { fprintf(stderr, "cannot read %s\n", path); exit(1); }
-    const int cflavour = strchr(path, 'C') != NULL;                    /* gofinal_ltfb.m:35 */
+    /* "a C in the name = written by the C++ program" exists in gofinal_ltfb.m:35 only (gofinal_op.m always takes the
+     * Octave variables); the reference tests the whole path string, here the FILE name, so that a directory such as
+     * /home/Claudio/ does not flip the flavour */
+    const char* base = strrchr(path, '/');
+    base = base ? base + 1 : path;
+    const int cflavour = ltfb && strchr(base, 'C') != NULL;
     memset(s, 0, sizeof *s);
     size_t n = 0;
     const double *c1 = need(&mf, "correction1_a", "correction1", &n), *d1 = need(&mf, "df1", NULL, &n);
@@ -120,11 +125,13 @@ static int reduce_station(int ltfb, const char* local, const char* remote, doubl
 {
     const double fs = 5e6, nint3 = 3.0;
     station lo, re;
-    load_station(local, 1, &lo);
-    load_station(remote, 0, &re);
+    load_station(local, 1, ltfb, &lo);
+    load_station(remote, 0, ltfb, &re);
     const size_t n = lo.n;
     if (n == 0) { fprintf(stderr, "empty result file\n"); return 1; }
-    const double dateini = end_epoch - (double)n;                       /* :48 / :33 */
+    /* gofinal_ltfb.m:48 dateini=dateltfb-length(indice1) of the LOCAL file; gofinal_op.m:36-37 takes length(indice1)
+     * while the REMOTE file is the one loaded */
+    const double dateini = end_epoch - (double)(ltfb ? n : re.n);
     double mx = -INFINITY;
     for (size_t p = 0; p < n; p++) if (lo.snr1[p] > mx) mx = lo.snr1[p];
     size_t* ind = (size_t*)malloc(sizeof(size_t) * n);

@@ -54,7 +54,8 @@ struct Backend {
     const char* err_string() const { return "emulation backend error"; }
     int init(int) { return 0; }
     void shutdown() {}
-    void use() {}
+    bool oom = false;
+    void use() { oom = false; }
     void* alloc(size_t bytes) { return calloc(bytes ? bytes : 1, 1); }
     void free(void* p) { ::free(p); }
     void zero(void* p, size_t bytes) { memset(p, 0, bytes); }

@@ -40,6 +40,12 @@ def test_cpp_whole_file_estimator(s, foffset, remote):
     pc.run_decimated_estimator(pc.EMU_LIB, m=10000, s=s, foffset=foffset, remote=remote)
 
 
+def test_cpp_whole_file_estimator_raw_mean_with_offset():
+    """main.cpp:381-420 subtracts the mean of the RAW samples from the derotated ones: with a large DC term and
+    foffset != 0 that leaves a strong tone at -foffset which the estimator must see exactly as the reference does."""
+    pc.run_decimated_estimator(pc.EMU_LIB, m=10000, s=4, foffset=1500.0, remote=0, dc=900.0 - 650.0j, check_carrier=False)
+
+
 @pytest.mark.parametrize("n", [10000, 200000, 250000])
 def test_fast_peak_path_matches_the_oracle(n):
     pc.run_variant_g(pc.EMU_LIB, n, seeds=(11, 12, 13), fast=True)

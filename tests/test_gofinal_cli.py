@@ -86,6 +86,18 @@ def test_octave_flavour(exe, tmp_path, mode):
     assert len(rows) == (200 if mode == "op" else 193)        # ltfb keeps SNR1 > max-10 dB only
 
 
+def test_op_mode_ignores_a_C_in_the_path_and_dates_from_the_remote_file(exe, tmp_path):
+    """gofinal_op.m has no C++-flavour branch (only gofinal_ltfb.m:35 does) and takes dateini from length(indice1) of
+    the REMOTE file (gofinal_op.m:36-37): a directory named Claudio/ must not flip the flavour, and a remote file
+    with more records than the local one shifts every epoch."""
+    lo, re = _files(np.random.default_rng(8), 200)
+    _, re_long = _files(np.random.default_rng(9), 230)
+    sub = tmp_path / "Claudio"
+    sub.mkdir()
+    rows = _run(exe, sub, "op", lo, re_long, "1671606192.mat", "remote1671606192.mat")
+    assert len(rows) == 200 and rows[0][0] == int(END - 230)
+
+
 def test_cpp_flavour_files(exe, tmp_path):
     """A 'C' in the path selects correction = indice0+corr and SNR in dB (gofinal_ltfb.m:35-45)."""
     lo, re = _files(np.random.default_rng(4), 180, cflavour=True)

@@ -113,6 +113,11 @@ def test_cpp_whole_file_estimator(m, s, foffset, remote):
     pc.run_decimated_estimator(pc.CUDA_LIB, m=m, s=s, foffset=foffset, remote=remote)
 
 
+def test_cpp_whole_file_estimator_raw_mean_with_offset():
+    """Large DC term and foffset != 0: the raw mean is subtracted after the derotation (main.cpp:381-420)."""
+    pc.run_decimated_estimator(pc.CUDA_LIB, m=200000, s=3, foffset=2500.0, remote=0, dc=900.0 - 650.0j, check_carrier=False)
+
+
 def test_qpsk_x4_estimator_and_complex_replica():
     """configs[2]: QPSK, x^4 estimator, 100 kchip/s code (N = 200 000)."""
     pc.run_qpsk(pc.CUDA_LIB)
