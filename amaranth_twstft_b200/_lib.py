@@ -23,7 +23,8 @@ EXPORTS = [
     "twstft_host_free", "twstft_device_alloc", "twstft_device_free", "twstft_copy_to_device",
     "twstft_copy_to_host", "twstft_synchronize", "twstft_kernel_launches", "twstft_debug_fetch",
     "twstft_window_bins", "twstft_doppler_bank", "twstft_search_df", "twstft_estimate_carrier_block", "twstft_estimate_bins",
-    "twstft_search_df_block", "twstft_estimate_decimated", "twstft_fast_counters", "twstft_timer_start", "twstft_timer_stop", "twstft_profile_enable", "twstft_profile_read",
+    "twstft_search_df_block", "twstft_estimate_decimated", "twstft_processing_cf64", "twstft_processing_cf64_df",
+    "twstft_search_df_cf64", "twstft_fast_counters", "twstft_timer_start", "twstft_timer_stop", "twstft_profile_enable", "twstft_profile_read",
 ]
 
 
@@ -85,6 +86,9 @@ def load(path=None):
     lib.twstft_search_df.argtypes = [P, P, C.c_int, C.c_size_t, C.c_int64, C.c_double, P, P, P]
     lib.twstft_estimate_carrier_block.argtypes = [P, P, C.c_int, C.c_size_t, C.c_int, P, P]
     lib.twstft_search_df_block.argtypes = [P, P, P, C.c_int, C.c_int, C.c_double, P, P, P]
+    lib.twstft_processing_cf64.argtypes = [P, P, C.c_size_t, C.c_int64, C.c_int64, P]
+    lib.twstft_processing_cf64_df.argtypes = [P, P, C.c_size_t, P, P]
+    lib.twstft_search_df_cf64.argtypes = [P, P, P, C.c_int, C.c_int64, C.c_int64, C.c_double, P, P, P]
     lib.twstft_estimate_bins.argtypes = [P, P, C.c_int, C.c_size_t, C.c_int64, C.c_int, P]
     lib.twstft_fast_counters.argtypes = [P, P, P]
     lib.twstft_estimate_decimated.argtypes = [P, P, C.c_size_t, C.c_int, C.c_double, C.c_int, P, P]

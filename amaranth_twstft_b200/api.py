@@ -156,6 +156,48 @@ class Correlator:
                     "twstft_process_windows")
         return out
 
+    # ------------------------------------------------------------------ the Octave function seam (complex double windows)
+    def _windows_cf64(self, d):
+        d = np.ascontiguousarray(d, dtype=np.complex128).reshape(-1)
+        if d.size % self.N:
+            raise ValueError(f"input holds {d.size} complex samples, not a multiple of one window ({self.N})")
+        return d, d.size // self.N
+
+    def processing(self, d, k=None, df=None):
+        """The reference's `processing` function on complex double window(s) whose mean the caller has removed.
+          processing(d, k)        variant G, godual_ranging.m:12: k = 1-based indices into the fftshift'ed spectrum
+                                  (a contiguous range, as k=find(...) gives; None: the plan's window)
+          processing(d, df=df)    variant K, claudio_aligned_code_lo_separate.m:24 / ..._re_separate.m:48
+        Returns one row per window."""
+        d, nwin = self._windows_cf64(d)
+        out = np.zeros(nwin, dtype=RESULT_DTYPE)
+        if df is not None:
+            dfa = np.ascontiguousarray(np.broadcast_to(np.asarray(df, dtype=np.float64).reshape(-1), (nwin,)))
+            self._check(self.lib.twstft_processing_cf64_df(self._plan, d.ctypes.data, nwin, dfa.ctypes.data,
+                                                           out.ctypes.data), "twstft_processing_cf64_df")
+            return out
+        k1, k2 = (0, 0) if k is None else (int(k[0]), int(k[-1]))
+        if k is not None and k2 - k1 + 1 != len(k):
+            raise ValueError("k must be a contiguous index range")
+        self._check(self.lib.twstft_processing_cf64(self._plan, d.ctypes.data, nwin, k1, k2, out.ctypes.data),
+                    "twstft_processing_cf64")
+        return out
+
+    def search_df_cf64(self, cor, d, k=None, df_threshold=20.0, ls=2):
+        """k=search_df(d,k,df_threshold) on the complex double block the re/ranging scripts hand over
+        (claudio_aligned_code_re_separate.m:26,150).  Returns (kbon, df, ncand)."""
+        d = np.ascontiguousarray(d, dtype=np.complex128).reshape(-1)
+        if d.size != self.N * ls:
+            raise ValueError("search_df takes exactly one block of ls*N samples")
+        kbon = np.zeros(1, dtype=np.int64)
+        df = np.zeros(1)
+        ncand = np.zeros(1, dtype=np.int32)
+        k1, k2 = (0, 0) if k is None else (int(k[0]), int(k[-1]))
+        self._check(self.lib.twstft_search_df_cf64(self._plan, cor._plan, d.ctypes.data, int(ls), k1, k2,
+                                                   float(df_threshold), kbon.ctypes.data, df.ctypes.data,
+                                                   ncand.ctypes.data), "twstft_search_df_cf64")
+        return int(kbon[0]), float(df[0]), int(ncand[0])
+
     def estimate_decimated(self, iq, dec=25, foffset=0.0, remote=0):
         """GoRanging::df (processing/CPP/main.cpp:363-450): whole-file estimator on one instant out of `dec`.
         Returns (df[nch], pos[nch]); entries of channels not looked at (remote) stay 0 / -1."""

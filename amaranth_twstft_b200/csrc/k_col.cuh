@@ -65,7 +65,7 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
         return MODE == COL_INV_ARGMAX ? "col_inv_argmax" : MODE == COL_INV_ARGMAX_STATS ? "col_inv_argmax_stats"
              : MODE == COL_INV_ARGMAX_K2 ? "col_inv_argmax_k2"
              : MODE == COL_INV_STORE ? "col_inv_store"
-             : SRC == SRC_RAW ? "col_fwd_raw" : SRC == SRC_BITS ? "col_fwd_bits" : "col_fwd_cf32";
+             : SRC == SRC_RAW ? "col_fwd_raw" : SRC == SRC_BITS ? "col_fwd_bits" : OP != 0 ? "col_fwd_cf32_op" : "col_fwd_cf32";
     }
     static constexpr bool PERSISTENT = true;
     static constexpr int NTA = S::NTS * TS;
@@ -166,6 +166,29 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
                                                         : cmul(csub(pa, pb), lr[S::NTS * b + m * S::SP0]);
                     }
                 }
+        } else if (SRC == SRC_CF32 && MODE == COL_FWD && OP != 0) {
+            // complex-float windows handed over by a caller that already holds them in floating point (the Octave
+            // seam processing(d,k): `d` is a complex column, godual_ranging.m:12): same pre-transform operations as
+            // the int16 path, window base from rec_offset / rec_stride (in samples), no mean handling (the caller
+            // of processing() removes the mean before the call, godual_ranging.m:80,94)
+            const i64 rbase = p.rec_offset ? p.rec_offset[wk.y] : (i64)wk.y * p.rec_stride;
+            const float2* gsrc = reinterpret_cast<const float2*>(p.src) + rbase + (i64)j * n2of(p) + col;
+            const i64 bstride = (i64)S::NTS * n2of(p), mstride = (i64)S::SP0 * n2of(p);
+            const float2* lr = p.lrow + (i64)wk.y * S::L + j;
+#pragma unroll
+            for (int b = 0; b < NB0; b++)
+#pragma unroll
+                for (int m = 0; m < S::R0; m++) {
+                    const float2 x = gsrc[b * bstride + m * mstride];
+                    if (SPLIT == 0) {
+                        r.v[b * S::R0 + m] = pre_op(x, OP == 1 ? lr[S::NTS * b + m * S::SP0] : x);
+                    } else {
+                        const float2 x2 = gsrc[p.half_stride + b * bstride + m * mstride];
+                        const float2 pa = power_op(x), pb = power_op(x2);
+                        r.v[b * S::R0 + m] = SPLIT == 1 ? cadd(pa, pb)
+                                                        : cmul(csub(pa, pb), lr[S::NTS * b + m * S::SP0]);
+                    }
+                }
         } else if (SRC == SRC_CF32) {
             const float2* gsrc = reinterpret_cast<const float2*>(p.src) + (i64)wk.y * p.N + (i64)j * n2of(p) + col;
             const i64 bstride = (i64)S::NTS * n2of(p), mstride = (i64)S::SP0 * n2of(p);
@@ -204,7 +227,7 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
             for (int b = 0; b < NBL; b++) {
                 const int jb = j + S::NTS * b;
                 base[b] = cis_cycles(-(double)((i64)n2 * jb) * p.invN);
-                if (SRC == SRC_RAW && USE_LROW) base[b] = cmul(base[b], p.lcol[lane * n2of(p) + n2]);
+                if ((SRC == SRC_RAW || SRC == SRC_CF32) && USE_LROW) base[b] = cmul(base[b], p.lcol[lane * n2of(p) + n2]);
             }
             const i64 bstr = (i64)S::NTS * n2of(p), mstr = (i64)S::NSLAST * n2of(p);
             float2* dj = d + (i64)j * n2of(p);

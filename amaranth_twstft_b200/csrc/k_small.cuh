@@ -34,6 +34,31 @@ HD double add_rn(double a, double b)
 }
 
 // ------------------------------------------------------------------------------------------------
+// KCvtF64: complex double -> complex float, for callers that hold their windows in floating point already (the
+// Octave seam processing(d,k), godual_ranging.m:12: `d` is a complex double column).
+struct CvtParams {
+    const double2* src;
+    float2* dst;
+    i64 n;
+};
+struct KCvtF64 {
+    typedef CvtParams Params;
+    static const char* name() { return "cvt_f64"; }
+    static constexpr bool PERSISTENT = false;
+    static constexpr int NT = 256, MINB = 4, NPH = 1, NSUM = 1;
+    struct Regs { u64 key; double dsum[NSUM]; };
+    static HD constexpr size_t smem_bytes() { return RED_SCRATCH_BYTES; }
+    static HD constexpr int sync_after(int) { return SYNC_BARRIER; }
+    template <int PH> static HD void phase(const Params& p, const Blk& blk, int tid, Regs&, unsigned char*)
+    {
+        for (i64 i = (i64)blk.x * NT + tid; i < p.n; i += (i64)blk.gx * NT) {
+            const double2 v = p.src[i];
+            p.dst[i] = make_float2((float)v.x, (float)v.y);
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
 // KMean: exact sums of I and Q over each window (godual_ranging.m:80 d1=d1-mean(d1); the means are
 // applied inside the column pass).  Sums of int16 over <= 1e7 samples stay below 2^53, so double
 // accumulation (and double atomics, in any order) is exact.

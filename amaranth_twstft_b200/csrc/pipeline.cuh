@@ -30,6 +30,8 @@ struct EstimatorCfg {
 };
 
 struct RunArgs {
+    const float2* d_cf = nullptr;   // complex-float windows instead of int16 records (one channel, mean already
+                               // removed by the caller): rec_stride / d_rec_offset count samples
     const short2* d_raw;
     int nrec;
     int nch;
@@ -274,6 +276,7 @@ public:
     {
         const int lanes = a.nrec * a.nch;
         be->zero(d_sums, (size_t)lanes * 2 * sizeof(double));
+        if (a.d_cf) return;        // complex-float windows arrive mean-removed (godual_ranging.m:80,94): sums stay 0
         MeanParams m{};
         m.src = a.d_raw; m.nelem = N * a.nch; m.nch = a.nch; m.rec_stride = a.rec_stride;
         m.rec_offset = a.d_rec_offset; m.sums = d_sums;
@@ -293,7 +296,11 @@ public:
         c.sub_mean = sub_mean; c.sums = d_sums; c.lrow = d_lrow; c.lcol = d_lcol;
         c.rec_stride = a.rec_stride; c.rec_offset = a.d_rec_offset; c.nq = 1;
         c.ntx = NCOLTILE * a.nch; c.ny = a.nrec;
-        if (a.nch == 2) {
+        if (a.d_cf) {
+            c.src = a.d_cf; c.sub_mean = 0; c.nch = 1; c.ntx = NCOLTILE;
+            typedef KCol<CS, TS, SRC_CF32, COL_FWD, OP, N2, 1> KC;
+            be->template launch<KC>(pgrid<KC>((i64)c.ntx * c.ny), c);
+        } else if (a.nch == 2) {
             typedef KCol<CS, TS, SRC_RAW, COL_FWD, OP, N2, 2> KC;
             be->template launch<KC>(pgrid<KC>((i64)c.ntx * c.ny), c);
         } else {
@@ -414,6 +421,7 @@ public:
     {
         const int lanes = a.nrec * a.nch;
         if (lanes > max_lanes) return -2;
+        if (a.d_cf) return -4;                                     // the angle kernel reads the int16 records
         const i64 third = (i64)floor(a.fs) / 3;                    // fs//3
         const int step = 10;
         const i64 My = ((third < N ? third : N) + step - 1) / step;   // len(y[0:fs//3:10])
@@ -609,6 +617,7 @@ public:
 inline IPipe* make_pipe(i64 n)
 {
     typedef FFTSpec<20, 20, 20> R8000;
+    typedef FFTSpec<20, 2, 20> R800;       // first radix == last radix, as the fused correlator row pass needs
     typedef FFTSpec<20, 20> R400;
     switch (n) {
 #ifndef TWSTFT_TS_FWD
@@ -620,6 +629,10 @@ inline IPipe* make_pipe(i64 n)
     case 200000: return new Pipe<FFTSpec<25>, R8000, 1, 64>();         // 100 kchip/s code windows
     case 250000: return new Pipe<FFTSpec<25, 25>, R400, 5, 16>();      // test size (same column kernel as 5e6)
     case 10000: return new Pipe<FFTSpec<25>, R400, 5, 16>();           // 5 kchip codes / test size
+    // the other code lengths shipped under experiments/221207_twoway_codes/codes (x2 samples per chip)
+    case 500000: return new Pipe<FFTSpec<25, 25>, R800, 5, 16, 8>();   // 250 kchip codes (noiselen250000_bitlen18_*)
+    case 50000: return new Pipe<FFTSpec<5, 25>, R400, 5, 16>();        // 25 kchip codes  (noiselen25000_bitlen17_*)
+    case 20000: return new Pipe<FFTSpec<25>, R800, 5, 16>();           // 10 kchip codes  (noiselen10000_bitlen14_*)
 #endif
     default: return nullptr;
     }

@@ -31,6 +31,9 @@ struct twstft_plan {
     unsigned char* d_bits = nullptr;
     size_t bits_cap = 0;
     long long fast_records = 0, fast_rerun = 0;   // records through the fast peak path / re-run through the full path
+    double2* d_cf64 = nullptr;     // upload staging of the complex-double entry points (one chunk)
+    float2* d_cf32 = nullptr;      // their windows as complex float
+    size_t cf64_cap = 0, cf32_cap = 0;   // samples
     std::string err;
 };
 
@@ -147,6 +150,8 @@ void twstft_plan_destroy(twstft_plan* p)
     p->be.free(p->d_dfin);
     p->be.free(p->d_off);
     p->be.free(p->d_bits);
+    p->be.free(p->d_cf64);
+    p->be.free(p->d_cf32);
     p->be.shutdown();
     delete p;
 }
@@ -518,23 +523,25 @@ static const short2* stage_window(twstft_plan* p, const int16_t* iq, int on_devi
 }
 
 static int run_bank(twstft_plan* p, const short2* d_win, const double* dfs, size_t nbins, int sub_mean,
-                    twstft_bank_result* results)
+                    twstft_bank_result* results, const float2* cf_win = nullptr)
 {
+    const int nch_src = cf_win ? 1 : p->nch;
     const int B = p->cfg.max_batch;
     std::vector<i64> off(B, 0);
     std::vector<double> dfl((size_t)B * p->nch);
     p->be.h2d(p->d_off, off.data(), sizeof(i64) * B);
+    p->be.sync();          // `off` is a local
     BankRow* d_rows = (BankRow*)p->d_res;                // the result staging is large enough: Result > BankRow
     for (size_t b0 = 0; b0 < nbins; b0 += B) {
         const int nb = (int)((nbins - b0) < (size_t)B ? (nbins - b0) : B);
         for (int i = 0; i < nb; i++)
-            for (int c = 0; c < p->nch; c++) dfl[(size_t)i * p->nch + c] = dfs[b0 + i];
-        p->be.h2d(p->d_dfin, dfl.data(), sizeof(double) * nb * p->nch);
+            for (int c = 0; c < nch_src; c++) dfl[(size_t)i * nch_src + c] = dfs[b0 + i];
+        p->be.h2d(p->d_dfin, dfl.data(), sizeof(double) * nb * nch_src);
         RunArgs a{};
-        a.d_raw = d_win; a.nrec = nb; a.nch = p->nch; a.rec_stride = 0; a.d_rec_offset = p->d_off;
+        a.d_raw = d_win; a.d_cf = cf_win; a.nrec = nb; a.nch = nch_src; a.rec_stride = 0; a.d_rec_offset = p->d_off;
         a.estimate = 0; a.d_df_in = p->d_dfin; a.variant = 1; a.ddof = 1; a.fs = p->cfg.fs;
-        if (p->pipe->bank(a, sub_mean, d_rows) != 0) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
-        p->be.d2h(results + b0 * p->nch, d_rows, sizeof(BankRow) * nb * p->nch);
+        if (p->pipe->bank(a, cf_win ? 0 : sub_mean, d_rows) != 0) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
+        p->be.d2h(results + b0 * nch_src, d_rows, sizeof(BankRow) * nb * nch_src);
         p->be.sync();
         if (!p->be.ok()) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
     }
@@ -557,31 +564,33 @@ int twstft_doppler_bank(twstft_plan* p, const int16_t* iq, int iq_on_device, siz
 // Body of search_df (claudio_aligned_code_re_separate.m:26-46).  `sp` owns the x^p spectrum (its estimator window
 // on the ls-block axis), `cp` owns the code and runs the per-candidate correlation on the window at d_win.
 static int search_df_core(twstft_plan* sp, const short2* d_blk, int ls, twstft_plan* cp, const short2* d_win,
-                          double df_threshold, int64_t* kbon, double* df_found, int32_t* ncand)
+                          double df_threshold, int64_t* kbon, double* df_found, int32_t* ncand,
+                          const float2* cf_blk = nullptr, const float2* cf_win = nullptr, const EstimatorCfg* e_over = nullptr)
 {
-    const EstimatorCfg& e = ls == 2 ? sp->est2 : sp->est;
+    const EstimatorCfg& e = e_over ? *e_over : (ls == 2 ? sp->est2 : sp->est);
     const size_t wlen = (size_t)(e.win_hi - e.win_lo + 1);
+    const int nch_src = cf_blk ? 1 : sp->nch;
     sp->be.use();
-    float* d_mag = (float*)sp->be.alloc(sizeof(float) * wlen * sp->nch);
+    float* d_mag = (float*)sp->be.alloc(sizeof(float) * wlen * nch_src);
     if (!sp->be.ok()) return fail(sp, TWSTFT_E_NOMEM, "device allocation failed");
     i64 zero = 0;
     sp->be.h2d(sp->d_off, &zero, sizeof(i64));
     RunArgs a{};
-    a.d_raw = d_blk; a.nrec = 1; a.nch = sp->nch; a.rec_stride = 0; a.d_rec_offset = sp->d_off;
+    a.d_raw = d_blk; a.d_cf = cf_blk; a.nrec = 1; a.nch = nch_src; a.rec_stride = 0; a.d_rec_offset = sp->d_off;
     a.estimate = 1; a.variant = sp->cfg.variant; a.ddof = sp->cfg.ddof; a.fs = sp->cfg.fs;
     int rc = TWSTFT_OK;
-    std::vector<float> mag(wlen * sp->nch);
+    std::vector<float> mag(wlen * nch_src);
     const int src = ls == 2 ? sp->pipe->window_spectrum_block2(a, e, d_mag) : sp->pipe->window_spectrum(a, e, d_mag);
     if (src != 0) rc = fail(sp, TWSTFT_E_CUDA, sp->be.err_string());
     if (rc == TWSTFT_OK) {
-        sp->be.d2h(mag.data(), d_mag, sizeof(float) * wlen * sp->nch);
+        sp->be.d2h(mag.data(), d_mag, sizeof(float) * wlen * nch_src);
         sp->be.sync();
         if (!sp->be.ok()) rc = fail(sp, TWSTFT_E_CUDA, sp->be.err_string());
     }
     sp->be.free(d_mag);
     if (rc != TWSTFT_OK) return rc;
     cp->be.use();
-    for (int c = 0; c < sp->nch; c++) {
+    for (int c = 0; c < nch_src; c++) {
         // ktmp=find(d2(k) > median(d2(k))*df_threshold)   re_separate.m:29
         std::vector<double> v(wlen);
         for (size_t i = 0; i < wlen; i++) v[i] = sqrt((double)mag[(size_t)c * wlen + i]);
@@ -598,11 +607,12 @@ static int search_df_core(twstft_plan* sp, const short2* d_blk, int ls, twstft_p
         if (cand.empty() || cand.size() >= 100) continue;          // re_separate.m:31
         std::vector<double> dfs(cand.size());
         for (size_t i = 0; i < cand.size(); i++) dfs[i] = axis_value(e, cand[i]) / (double)e.power;
-        std::vector<twstft_bank_result> rows(cand.size() * cp->nch);
-        rc = run_bank(cp, d_win, dfs.data(), dfs.size(), e.sub_mean, rows.data());   // y=d(1:length(fcode)).*lo (:35)
+        const int nch_b = cf_win ? 1 : cp->nch;
+        std::vector<twstft_bank_result> rows(cand.size() * nch_b);
+        rc = run_bank(cp, d_win, dfs.data(), dfs.size(), e.sub_mean, rows.data(), cf_win);   // y=d(1:length(fcode)).*lo (:35)
         if (rc != TWSTFT_OK) return rc;
         for (size_t i = 0; i < cand.size(); i++)
-            if (rows[i * cp->nch + c].metric > 100.0) {            // "SNR > 20 dB", last accepted wins (:42)
+            if (rows[i * nch_b + c].metric > 100.0) {            // "SNR > 20 dB", last accepted wins (:42)
                 kbon[c] = cand[i] + 1;
                 if (df_found) df_found[c] = dfs[i];
             }
@@ -643,6 +653,121 @@ int twstft_search_df_block(twstft_plan* est, twstft_plan* cor, const int16_t* iq
         d_blk = est->d_raw;
     }
     const int rc = search_df_core(est, d_blk, ls, cor, d_blk, df_threshold, kbon, df_found, ncand);
+    if (rc != TWSTFT_OK && cor != est && cor->err.size() && est->err.empty()) est->err = cor->err;
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Octave function seam: the windows arrive as complex doubles, mean already removed by the caller
+// (godual_ranging.m:12,80,94; claudio_aligned_code_lo_separate.m:24,132; ..._re_separate.m:26,48)
+
+// grow the complex-float window buffer / the complex-double upload staging to `n32` / `n64` samples
+static int ensure_cf(twstft_plan* p, size_t n32, size_t n64)
+{
+    if (p->cf32_cap < n32) {
+        p->be.sync();
+        p->be.free(p->d_cf32);
+        p->d_cf32 = (float2*)p->be.alloc(sizeof(float2) * n32);
+        p->cf32_cap = p->d_cf32 ? n32 : 0;
+    }
+    if (p->cf64_cap < n64) {
+        p->be.sync();
+        p->be.free(p->d_cf64);
+        p->d_cf64 = (double2*)p->be.alloc(sizeof(double2) * n64);
+        p->cf64_cap = p->d_cf64 ? n64 : 0;
+    }
+    return (p->cf32_cap >= n32 && p->cf64_cap >= n64 && p->be.ok()) ? 0 : -1;
+}
+
+// host complex doubles [n] -> device complex floats at dst (through the upload staging, `chunk` samples at a time)
+static void upload_cf64(twstft_plan* p, const double* host, size_t n, float2* dst)
+{
+    const size_t chunk = p->cf64_cap;
+    for (size_t i0 = 0; i0 < n; i0 += chunk) {
+        const size_t m = (n - i0) < chunk ? (n - i0) : chunk;
+        p->be.h2d(p->d_cf64, host + 2 * i0, sizeof(double2) * m);
+        CvtParams c{};
+        c.src = p->d_cf64; c.dst = dst + i0; c.n = (i64)m;
+        i64 nblk = ((i64)m + KCvtF64::NT - 1) / KCvtF64::NT;
+        const i64 wave = (i64)p->be.num_sms * 8;
+        if (nblk > wave) nblk = wave;
+        p->be.launch<KCvtF64>(dim3((unsigned)nblk, 1, 1), c);
+    }
+}
+
+static int processing_cf_core(twstft_plan* p, const double* d, size_t nwin, const EstimatorCfg* est, const double* df,
+                              twstft_result* results)
+{
+    if (!p->have_code) return fail(p, TWSTFT_E_NOCODE, "no PRN code installed (twstft_set_code / twstft_gen_code)");
+    if (p->cfg.fine_freq) return fail(p, TWSTFT_E_ARG, "fine_freq needs the int16 records (twstft_process)");
+    const size_t N = (size_t)p->cfg.nsamples, B = (size_t)p->cfg.max_batch;
+    const size_t perbatch = B * (size_t)p->nch;                 // the plan has room for max_batch * nch lanes
+    if (ensure_cf(p, N * perbatch, N) != 0) return fail(p, TWSTFT_E_NOMEM, "device allocation failed");
+    for (size_t w0 = 0; w0 < nwin; w0 += perbatch) {
+        const int nb = (int)((nwin - w0) < perbatch ? (nwin - w0) : perbatch);
+        upload_cf64(p, d + 2 * w0 * N, (size_t)nb * N, p->d_cf32);
+        RunArgs a{};
+        a.d_cf = p->d_cf32; a.d_raw = nullptr; a.nrec = nb; a.nch = 1; a.rec_stride = (i64)N; a.d_rec_offset = nullptr;
+        a.estimate = est ? 1 : 0; a.variant = p->cfg.variant; a.ddof = p->cfg.ddof; a.fs = p->cfg.fs; a.d_out = p->d_res;
+        a.allow_fast = 0;
+        if (est) {
+            if (p->pipe->estimate(a, *est) != 0) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
+        } else {
+            p->be.h2d(p->d_dfin, df + w0, sizeof(double) * nb);
+            a.d_df_in = p->d_dfin;
+        }
+        if (p->pipe->correlate(a) != 0) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
+        p->be.d2h(results + w0, p->d_res, sizeof(Result) * nb);
+        p->be.sync();
+        if (!p->be.ok()) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
+    }
+    return TWSTFT_OK;
+}
+
+int twstft_processing_cf64(twstft_plan* p, const double* d, size_t nwin, int64_t k_first, int64_t k_last,
+                           twstft_result* results)
+{
+    if (!p || !p->pipe || !d || !results) return TWSTFT_E_ARG;
+    p->be.use();
+    EstimatorCfg e = p->est;
+    e.sub_mean = 0;                        // the caller removed the mean (godual_ranging.m:80,94)
+    if (k_first > 0) {                     // k(1) .. k(end), 1-based on the fftshift'ed axis
+        if (k_last < k_first || k_last > e.naxis) return fail(p, TWSTFT_E_ARG, "estimator window outside the spectrum");
+        e.win_lo = k_first - 1;
+        e.win_hi = k_last - 1;
+    }
+    return processing_cf_core(p, d, nwin, &e, nullptr, results);
+}
+
+int twstft_processing_cf64_df(twstft_plan* p, const double* d, size_t nwin, const double* df, twstft_result* results)
+{
+    if (!p || !p->pipe || !d || !df || !results) return TWSTFT_E_ARG;
+    p->be.use();
+    return processing_cf_core(p, d, nwin, nullptr, df, results);
+}
+
+int twstft_search_df_cf64(twstft_plan* est, twstft_plan* cor, const double* d, int ls, int64_t k_first, int64_t k_last,
+                          double df_threshold, int64_t* kbon, double* df_found, int32_t* ncand)
+{
+    if (!est || !cor || !est->pipe || !cor->pipe || !d || !kbon || (ls != 1 && ls != 2)) return TWSTFT_E_ARG;
+    if (!cor->have_code) return fail(cor, TWSTFT_E_NOCODE, "no PRN code installed");
+    if (est->be.device != cor->be.device) return fail(est, TWSTFT_E_ARG, "estimator and correlator plans must share the device");
+    if (cor->cfg.nsamples > est->cfg.nsamples * ls)
+        return fail(est, TWSTFT_E_ARG, "the correlation window is longer than the block");
+    est->be.use();
+    EstimatorCfg e = ls == 2 ? est->est2 : est->est;
+    e.sub_mean = 0;                        // search_df squares the block as it is (re_separate.m:28)
+    if (k_first > 0) {
+        if (k_last < k_first || k_last > e.naxis) return fail(est, TWSTFT_E_ARG, "estimator window outside the spectrum");
+        e.win_lo = k_first - 1;
+        e.win_hi = k_last - 1;
+    }
+    const size_t nblk = (size_t)est->cfg.nsamples * ls;
+    if (ensure_cf(est, nblk, (size_t)est->cfg.nsamples) != 0) return fail(est, TWSTFT_E_NOMEM, "device allocation failed");
+    upload_cf64(est, d, nblk, est->d_cf32);
+    est->be.sync();                        // the correlator plan reads the same buffer on its own stream
+    const int rc = search_df_core(est, nullptr, ls, cor, nullptr, df_threshold, kbon, df_found, ncand,
+                                  est->d_cf32, est->d_cf32, &e);
     if (rc != TWSTFT_OK && cor != est && cor->err.size() && est->err.empty()) est->err = cor->err;
     return rc;
 }

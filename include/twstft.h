@@ -22,6 +22,13 @@
  *   twstft_search_df_block  the same on the 2-s block the scripts hand it                 claudio_aligned_code_re_separate.m:150
  *   twstft_estimate_bins d2=fftshift(abs(fft(d.^2))); max(d2(kbon-3:kbon+3)), d=[dold;block]  claudio_aligned_code_re_separate.m:166-168
  *   twstft_estimate_decimated  GoRanging::df: whole-file estimator on one instant out of 25            processing/CPP/main.cpp:363-450
+ *   twstft_processing_cf64     [indice,correction,SNRr,SNRi,df,puissance,...]=processing(d,k)   godual_ranging.m:12
+ *   twstft_processing_cf64_df  [xval,indice,correction,...]=processing(d,k,df) / processing(d,df)
+ *                                                     claudio_aligned_code_lo_separate.m:24, ..._re_separate.m:48
+ *   twstft_search_df_cf64      k=search_df(d,k,df_threshold)                      claudio_aligned_code_re_separate.m:26
+ *                        (the three take the complex double column `d` the Octave functions receive, mean already
+ *                         removed by the caller, and the index vector k as its 1-based first/last element: what
+ *                         processing/C/twstft_mex.c marshals)
  *   twstft_result        one row of the .mat variables                            godual_ranging.m:128-130, lo_separate.m:166
  *
  * Conventions: plain C, caller owns every host buffer, the plan owns device memory and streams,
@@ -138,6 +145,23 @@ int twstft_process_device(twstft_plan* plan, const int16_t* iq_dev, size_t nreco
  * device) buffer holding `total_instants` sample instants, derotated by the given df[i*nch+ch]. */
 int twstft_process_windows(twstft_plan* plan, const int16_t* iq, int iq_on_device, size_t total_instants,
                            const int64_t* offsets, const double* df, size_t nwin, twstft_result* results);
+
+/* The Octave FUNCTION seam.  `d`: nwin windows of N complex doubles (re, im interleaved: Octave's complex column),
+ * already mean-removed by the caller exactly as the scripts do before the call (godual_ranging.m:80,94;
+ * lo_separate.m:132); one channel per window, results[window].  The "globals" the Octave functions read
+ * (temps freq fcode code fs Nint) are the plan's configuration and installed code.
+ *   twstft_processing_cf64     variant G processing(d,k): k = k_first..k_last, the 1-based index range into the
+ *                              fftshift'ed spectrum (k_first <= 0: the plan's own window); estimates df, correlates
+ *   twstft_processing_cf64_df  variant K processing(d,k,df) / processing(d,df): df[window] given by the caller
+ * (fine_freq and the fast peak path are not offered here.) */
+int twstft_processing_cf64(twstft_plan* plan, const double* d, size_t nwin, int64_t k_first, int64_t k_last,
+                           twstft_result* results);
+int twstft_processing_cf64_df(twstft_plan* plan, const double* d, size_t nwin, const double* df, twstft_result* results);
+/* k=search_df(d,k,df_threshold) (claudio_aligned_code_re_separate.m:26-46,150): `d` = the block of ls*est->nsamples
+ * complex doubles as the script holds it (raw, not mean-removed), k_first..k_last 1-based on the block's fftshift'ed
+ * axis (<= 0: est's window); outputs as twstft_search_df_block, one channel. */
+int twstft_search_df_cf64(twstft_plan* est, twstft_plan* cor, const double* d, int ls, int64_t k_first, int64_t k_last,
+                          double df_threshold, int64_t* kbon, double* df_found, int32_t* ncand);
 
 /* Carrier estimator alone (A3): df[record*nch+ch], bins[...] = 0-based index on the shifted axis. */
 int twstft_estimate_carrier(twstft_plan* plan, const int16_t* iq, int iq_on_device, size_t nrecords,

@@ -20,6 +20,9 @@ TOL_SNR_DB = 0.01
 
 CODES = {  # window length -> (bitlen, taps, noiselen): all from experiments/221207_twoway_codes/codes
     10000: (13, 27, 5000),
+    20000: (14, 43, 10000),
+    50000: (17, 3, 25000),
+    500000: (18, 39, 250000),
     200000: (17, 9, 100000),
     250000: (17, 9, 125000),
     1000000: (19, 39, 500000),
@@ -424,3 +427,50 @@ def run_search_df_block(lib, fs=250000.0, n=10000, df=50321.5, seed=12, window=(
     kref, tried = oc.search_df(oc.unpack_single(raw), k, 20.0, freq, oc.fcode_K(code), fs=fs)
     assert ncand[0] == len(tried) and kref > 0, (ncand, tried)
     assert kbon[0] == kref and dff[0] == freq[kref - 1] / 2, (kbon, kref, dff)
+
+
+def run_octave_seam(lib, n, seeds=(51, 52), fs=5e6, window=(-20000.0, 20000.0)):
+    """The Octave FUNCTION seam: the very arguments `processing(d,k)` receives in godual_ranging.m:12,80,94 (a complex
+    double column whose mean the caller removed, and the 1-based index vector k) go to twstft_processing_cf64 and to
+    the oracle; K twin processing(d,k,df) of claudio_aligned_code_lo_separate.m:24 with the caller's df."""
+    bits, code = make_code(n)
+    freq = oc.freq_axis_G(fs, n)
+    k0 = oc.window(freq, *window)                       # 0-based; Octave's k is k0 + 1
+    ds = []
+    for s_ in seeds:
+        d1, d2 = oc.unpack_interleaved2(synth.record_pair(code, s_, fs=fs)[0])
+        ds += [d1 - d1.mean(), d2 - d2.mean()]
+    with Correlator(nsamples=n, fs=fs, layout="single", max_batch=3, lib=lib) as cor:     # 4 windows in batches of 3
+        cor.set_code(bits)
+        res = cor.processing(np.concatenate(ds), k=k0 + 1)
+        res_default = cor.processing(ds[0])             # k omitted: the plan's window (the same here)
+    for i, d in enumerate(ds):
+        ref = oc.processing_G(d, k0, freq, oc.fcode_G(code), code, fs)
+        assert_row_matches(res[i], ref, where=f"processing(d,k) N={n} window {i}")
+    assert res_default[0] == res[0]
+    dfk = 1234.5
+    raw, _ = synth.record_single(code, seeds[0], delay=777.25, df=dfk, snr_db=-5.0, fs=fs)
+    d = oc.unpack_single(raw)
+    d = d - d.mean()
+    with Correlator(nsamples=n, fs=fs, variant="K", layout="single", max_batch=2, lib=lib) as cor:
+        cor.set_code(bits)
+        rk = cor.processing(d, df=dfk)
+    assert_row_matches(rk[0], oc.processing_K(d, dfk, oc.fcode_K(code), code, fs), where=f"processing(d,k,df) N={n}")
+
+
+def run_octave_seam_search_df(lib, fs=250000.0, n=10000, df=50321.5, seed=12, window=(92000.0, 108000.0)):
+    """k=search_df(d,k,df_threshold) with the complex double block and the index vector of
+    claudio_aligned_code_re_separate.m:26,150."""
+    bits, code = make_code(n)
+    raw = synth.stream_single(code, int(2 * fs), seed, delay=1234.25, df=df, fs=fs, dc=(10.0, 5.0))
+    d = oc.unpack_single(raw)
+    freq = oc.freq_axis_K(fs, 2)
+    k = oc.window(freq, *window)
+    with Correlator(nsamples=int(fs), fs=fs, variant="K", layout="single", freq_axis="K", window_hz=(-1000.0, 1000.0),
+                    est_sub_mean=0, max_batch=1, lib=lib) as est, \
+            Correlator(nsamples=n, fs=fs, variant="K", layout="single", max_batch=8, lib=lib) as cor:
+        cor.set_code(bits)
+        kbon, dff, ncand = est.search_df_cf64(cor, d, k=k + 1, df_threshold=20.0, ls=2)   # the window comes from k
+    kref, tried = oc.search_df(d, k, 20.0, freq, oc.fcode_K(code), fs=fs)
+    assert ncand == len(tried) and kref > 0, (ncand, tried)
+    assert kbon == kref and dff == freq[kref - 1] / 2, (kbon, kref, dff)

@@ -24,6 +24,13 @@ def test_variant_g(n):
     pc.run_variant_g(pc.EMU_LIB, n, seeds=[11, 12, 13])
 
 
+@pytest.mark.parametrize("n,fast", [(20000, False), (50000, False), (50000, True), (20000, True)])
+def test_other_shipped_code_lengths(n, fast):
+    """N = 2 x {10 000, 25 000} chips (experiments/221207_twoway_codes/codes): the 800-point row transform
+    (radices 20.2.20) and the 5.25 column transform with the 400-point rows."""
+    pc.run_variant_g(pc.EMU_LIB, n, seeds=[21, 22], fast=fast)
+
+
 @pytest.mark.parametrize("name", ["n1e4", "n2e5"])
 def test_fine_frequency_against_reference_python_outputs(name):
     """A10 + the whole G path against tests/golden/ref_py_*.json (outputs of the reference's own numpy code)."""
@@ -259,3 +266,12 @@ def test_estimate_bins_any_length():
 def test_search_df_on_two_second_block():
     pc.run_search_df_block(pc.EMU_LIB)
     pc.run_search_df_block(pc.EMU_LIB, df=-3456.25, window=(-8000.0, 8000.0))      # ranging window
+
+
+@pytest.mark.parametrize("n", [10000, 250000])
+def test_octave_function_seam_processing(n):
+    pc.run_octave_seam(pc.EMU_LIB, n)
+
+
+def test_octave_function_seam_search_df():
+    pc.run_octave_seam_search_df(pc.EMU_LIB)

@@ -39,6 +39,13 @@ def test_variant_g_small(n):
     pc.run_variant_g(pc.CUDA_LIB, n, seeds=[11, 12, 13])
 
 
+@pytest.mark.parametrize("n,fast", [(20000, False), (50000, False), (500000, False), (500000, True), (50000, True)])
+def test_other_shipped_code_lengths(n, fast):
+    """N = 2 x {10 000, 25 000, 250 000} chips with the matching shipped LFSR codes
+    (experiments/221207_twoway_codes/codes/noiselen{10000,25000,250000}_*): 800-point rows (radices 20.2.20)."""
+    pc.run_variant_g(pc.CUDA_LIB, n, seeds=[21, 22], fast=fast)
+
+
 def test_variant_g_full_size():
     """configs[1]: two-channel 1-s records at 5 MS/s, 2.5 Mchip/s 22-bit code."""
     pc.run_variant_g(pc.CUDA_LIB, 5000000, seeds=[20261017, 20261018], max_batch=2)
@@ -209,3 +216,15 @@ def test_estimate_bins_any_length():
 def test_search_df_on_two_second_block():
     pc.run_search_df_block(pc.CUDA_LIB)
     pc.run_search_df_block(pc.CUDA_LIB, fs=5e6, n=200000)
+
+
+@pytest.mark.parametrize("n", [200000, 5000000])
+def test_octave_function_seam_processing(n):
+    """processing(d,k) / processing(d,k,df) with the complex double column the Octave functions receive
+    (godual_ranging.m:12, claudio_aligned_code_lo_separate.m:24) through twstft_processing_cf64{,_df}."""
+    pc.run_octave_seam(pc.CUDA_LIB, n, seeds=(51,) if n > 1000000 else (51, 52))
+
+
+def test_octave_function_seam_search_df():
+    pc.run_octave_seam_search_df(pc.CUDA_LIB)
+    pc.run_octave_seam_search_df(pc.CUDA_LIB, fs=5e6, n=200000, df=101234.5, window=(92000.0, 108000.0))
