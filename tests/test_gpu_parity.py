@@ -227,4 +227,4 @@ def test_octave_function_seam_processing(n):
 
 def test_octave_function_seam_search_df():
     pc.run_octave_seam_search_df(pc.CUDA_LIB)
-    pc.run_octave_seam_search_df(pc.CUDA_LIB, fs=5e6, n=200000, df=101234.5, window=(92000.0, 108000.0))
+    pc.run_octave_seam_search_df(pc.CUDA_LIB, fs=5e6, n=200000, df=50321.5, window=(92000.0, 108000.0))

@@ -128,4 +128,4 @@ def test_mex_processing_signatures_on_the_gpu(tmp_path):
 
 @pytest.mark.gpu
 def test_mex_search_df_on_the_gpu(tmp_path):
-    _check_search_df("cuda", tmp_path, 5e6, 200000, 101234.5)
+    _check_search_df("cuda", tmp_path, 5e6, 200000, 50321.5)
