@@ -24,7 +24,9 @@ EXPORTS = [
     "twstft_copy_to_host", "twstft_synchronize", "twstft_kernel_launches", "twstft_debug_fetch",
     "twstft_window_bins", "twstft_doppler_bank", "twstft_search_df", "twstft_estimate_carrier_block", "twstft_estimate_bins",
     "twstft_search_df_block", "twstft_estimate_decimated", "twstft_processing_cf64", "twstft_processing_cf64_df",
-    "twstft_search_df_cf64", "twstft_fast_counters", "twstft_timer_start", "twstft_timer_stop", "twstft_profile_enable", "twstft_profile_read",
+    "twstft_search_df_cf64", "twstft_shard_create", "twstft_shard_destroy", "twstft_shard_ngpus", "twstft_shard_plan",
+    "twstft_shard_last_error", "twstft_shard_set_code", "twstft_shard_process", "twstft_process_cycled",
+    "twstft_shard_process_cycled", "twstft_synth_records", "twstft_synth_stream", "twstft_fast_counters", "twstft_timer_start", "twstft_timer_stop", "twstft_profile_enable", "twstft_profile_read",
 ]
 
 
@@ -89,6 +91,20 @@ def load(path=None):
     lib.twstft_processing_cf64.argtypes = [P, P, C.c_size_t, C.c_int64, C.c_int64, P]
     lib.twstft_processing_cf64_df.argtypes = [P, P, C.c_size_t, P, P]
     lib.twstft_search_df_cf64.argtypes = [P, P, P, C.c_int, C.c_int64, C.c_int64, C.c_double, P, P, P]
+    lib.twstft_shard_create.argtypes = [C.POINTER(Config), P, C.c_int, C.POINTER(P)]
+    lib.twstft_shard_destroy.argtypes = [P]
+    lib.twstft_shard_destroy.restype = None
+    lib.twstft_shard_ngpus.argtypes = [P]
+    lib.twstft_shard_plan.argtypes = [P, C.c_int]
+    lib.twstft_shard_plan.restype = P
+    lib.twstft_shard_last_error.argtypes = [P]
+    lib.twstft_shard_last_error.restype = C.c_char_p
+    lib.twstft_shard_set_code.argtypes = [P, P, C.c_size_t, C.c_int]
+    lib.twstft_shard_process.argtypes = [P, P, C.c_size_t, P]
+    lib.twstft_process_cycled.argtypes = [P, P, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, P]
+    lib.twstft_shard_process_cycled.argtypes = [P, P, C.c_size_t, C.c_size_t, C.c_int, P, P, P]
+    lib.twstft_synth_records.argtypes = [P, C.c_uint64, C.c_size_t, C.c_double, C.c_double, P]
+    lib.twstft_synth_stream.argtypes = [P, C.c_uint64, C.c_size_t, C.c_double, C.c_double, C.c_double, P]
     lib.twstft_estimate_bins.argtypes = [P, P, C.c_int, C.c_size_t, C.c_int64, C.c_int, P]
     lib.twstft_fast_counters.argtypes = [P, P, P]
     lib.twstft_estimate_decimated.argtypes = [P, P, C.c_size_t, C.c_int, C.c_double, C.c_int, P, P]

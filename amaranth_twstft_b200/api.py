@@ -30,7 +30,8 @@ class Correlator:
 
     def __init__(self, nsamples=5000000, fs=5e6, variant="G", modulation="bpsk", layout="interleaved2",
                  window_hz=(-20000.0, 20000.0), freq_axis=None, nint=1, samples_per_chip=2, ddof=1,
-                 est_sub_mean=None, max_batch=4, device=0, lib=None, fine_freq=False, code_window=False, fast_peak=False):
+                 est_sub_mean=None, max_batch=4, device=0, lib=None, fine_freq=False, code_window=False, fast_peak=False,
+                 _plan=None):
         self.lib = _lib.load(lib)
         cfg = _lib.Config()
         self.lib.twstft_default_config(C.byref(cfg))
@@ -55,6 +56,10 @@ class Correlator:
         self.cfg = cfg
         self.nch = 2 if cfg.layout == _lib.LAYOUT_INTERLEAVED2 else 1
         self.N = int(nsamples)
+        self._owned = _plan is None
+        if _plan is not None:            # a plan owned by a Sharder
+            self._plan = _plan
+            return
         self._plan = C.c_void_p()
         rc = self.lib.twstft_plan_create(C.byref(cfg), C.byref(self._plan))
         if rc != 0:
@@ -68,7 +73,8 @@ class Correlator:
             self.lib.twstft_host_free(ptr)
         self._pinned = []
         if getattr(self, "_plan", None):
-            self.lib.twstft_plan_destroy(self._plan)
+            if getattr(self, "_owned", True):
+                self.lib.twstft_plan_destroy(self._plan)
             self._plan = C.c_void_p()
 
     def __del__(self):
@@ -320,6 +326,38 @@ class Correlator:
     def device_free(self, ptr):
         self.lib.twstft_device_free(self._plan, ptr)
 
+    def from_device(self, ptr, nbytes, dtype=np.int16):
+        out = np.zeros(nbytes // np.dtype(dtype).itemsize, dtype=dtype)
+        self._check(self.lib.twstft_copy_to_host(self._plan, out.ctypes.data, ptr, out.nbytes), "twstft_copy_to_host")
+        return out
+
+    # ------------------------------------------------------------------ synthetic inputs on the device (bench tooling)
+    def synth_records(self, seed0, nrecords, snr1_db=-5.0, snr2_db=0.6):
+        """nrecords synthetic records in the plan's layout, generated in device memory (k_synth.cuh); returns the
+        device pointer (free with device_free)."""
+        ptr = C.c_void_p()
+        nbytes = nrecords * self.N * self.nch * 4
+        self._check(self.lib.twstft_device_alloc(self._plan, nbytes, C.byref(ptr)), "twstft_device_alloc")
+        self._check(self.lib.twstft_synth_records(self._plan, int(seed0), nrecords, float(snr1_db), float(snr2_db), ptr),
+                    "twstft_synth_records")
+        return ptr
+
+    def synth_stream(self, seed, ninstants, delay=0.0, df=0.0, snr_db=-5.0):
+        ptr = C.c_void_p()
+        self._check(self.lib.twstft_device_alloc(self._plan, ninstants * 4, C.byref(ptr)), "twstft_device_alloc")
+        self._check(self.lib.twstft_synth_stream(self._plan, int(seed), int(ninstants), float(delay), float(df),
+                                                 float(snr_db), ptr), "twstft_synth_stream")
+        return ptr
+
+    def process_cycled(self, pool, pool_records, first_record, nrecords, on_device=False):
+        """nrecords records first_record.. drawn cyclically from a pool of pool_records records (host array or device
+        pointer): the day-of-data driver."""
+        out = np.zeros((nrecords, self.nch), dtype=RESULT_DTYPE)
+        ptr = pool if on_device else np.ascontiguousarray(pool, dtype=np.int16).ctypes.data
+        self._check(self.lib.twstft_process_cycled(self._plan, ptr, int(on_device), pool_records, first_record, nrecords,
+                                                   out.ctypes.data), "twstft_process_cycled")
+        return out
+
     def debug_fetch(self, what, lane, count, dtype):
         out = np.zeros(count, dtype=dtype)
         self._check(self.lib.twstft_debug_fetch(self._plan, what, lane, out.ctypes.data, out.nbytes), "twstft_debug_fetch")
@@ -329,3 +367,70 @@ class Correlator:
 def delay_samples(res):
     """Printed delay of godual_ranging.m:96-98 in samples: (indice-1+correction)/3."""
     return (res["indice"] - 1.0 + res["correction"]) / 3.0
+
+
+class Sharder:
+    """All GPUs of one box behind one object: one host thread + one plan per GPU inside the C library
+    (twstft_shard_*), GPU g of G takes records [g*R/G, (g+1)*R/G), rows land at their record index.
+    Mirrors the record loop of godual_ranging.m:75-102 / processing/CPP/main.cpp:452-519 over many GPUs."""
+
+    def __init__(self, ngpus, devices=None, lib=None, **cfg_kw):
+        probe = Correlator.__new__(Correlator)          # reuse the keyword -> twstft_config translation
+        Correlator.__init__(probe, lib=lib, _plan=C.c_void_p(0), **cfg_kw)
+        self.lib, self.cfg, self.nch, self.N = probe.lib, probe.cfg, probe.nch, probe.N
+        self._shard = C.c_void_p()
+        dev = (C.c_int * ngpus)(*devices) if devices is not None else None
+        rc = self.lib.twstft_shard_create(C.byref(self.cfg), dev, ngpus, C.byref(self._shard))
+        if rc != 0:
+            msg = self.lib.twstft_shard_last_error(self._shard).decode() if self._shard else "shard creation failed"
+            self.close()
+            raise TwstftError(f"twstft_shard_create failed ({rc}): {msg}")
+        self.ngpus = ngpus
+
+    def close(self):
+        if getattr(self, "_shard", None):
+            self.lib.twstft_shard_destroy(self._shard)
+            self._shard = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise TwstftError(f"{what} failed ({rc}): {self.lib.twstft_shard_last_error(self._shard).decode()}")
+
+    def plan(self, g):
+        """Correlator view of GPU g's plan (owned by the shard)."""
+        kw = dict(nsamples=self.N, lib=None)
+        c = Correlator.__new__(Correlator)
+        c.lib, c.cfg, c.nch, c.N = self.lib, self.cfg, self.nch, self.N
+        c._plan, c._owned, c._pinned = C.c_void_p(self.lib.twstft_shard_plan(self._shard, g)), False, []
+        return c
+
+    def set_code(self, chips, qpsk=False):
+        chips = np.ascontiguousarray(chips, dtype=np.uint8)
+        self._check(self.lib.twstft_shard_set_code(self._shard, chips.ctypes.data, chips.size, int(qpsk)),
+                    "twstft_shard_set_code")
+
+    def process(self, iq):
+        iq = np.ascontiguousarray(iq, dtype=np.int16)
+        per = 2 * self.nch * self.N
+        nrec = iq.size // per
+        out = np.zeros((nrec, self.nch), dtype=RESULT_DTYPE)
+        self._check(self.lib.twstft_shard_process(self._shard, iq.ctypes.data, nrec, out.ctypes.data), "twstft_shard_process")
+        return out
+
+    def process_cycled(self, pool, nrecords, resident=True):
+        """nrecords records drawn cyclically from the host pool; returns (rows, wall seconds, per-GPU device seconds)."""
+        pool = np.ascontiguousarray(pool, dtype=np.int16)
+        per = 2 * self.nch * self.N
+        out = np.zeros((nrecords, self.nch), dtype=RESULT_DTYPE)
+        wall = C.c_double()
+        dev = (C.c_double * self.ngpus)()
+        self._check(self.lib.twstft_shard_process_cycled(self._shard, pool.ctypes.data, pool.size // per, nrecords,
+                                                         int(bool(resident)), out.ctypes.data, C.byref(wall), dev),
+                    "twstft_shard_process_cycled")
+        return out, wall.value, list(dev)

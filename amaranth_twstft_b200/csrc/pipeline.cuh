@@ -18,6 +18,7 @@
 #include "k_col.cuh"
 #include "k_rowcorr.cuh"
 #include "k_small.cuh"
+#include "k_synth.cuh"
 
 namespace twstft {
 

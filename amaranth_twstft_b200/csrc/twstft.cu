@@ -5,7 +5,12 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <thread>
+#include <chrono>
 #include <stdio.h>
+#ifndef TWSTFT_EMU
+#include <sched.h>
+#endif
 
 using namespace twstft;
 
@@ -22,6 +27,8 @@ struct twstft_plan {
     int nq = 3;
     int max_lanes = 0;
     bool have_code = false;
+    int code_qpsk = 0;
+    size_t code_nchips = 0;
     short2* d_raw = nullptr;       // staging for host inputs: two slots of max_batch records
     size_t raw_elems_per_rec = 0;
     Result* d_res = nullptr;
@@ -206,6 +213,8 @@ static int install_code(twstft_plan* p, const unsigned char* host_bits, size_t n
     p->be.sync();
     if (!p->be.ok()) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
     p->have_code = true;
+    p->code_qpsk = qpsk;
+    p->code_nchips = nchips;
     return TWSTFT_OK;
 }
 
@@ -911,6 +920,258 @@ int twstft_estimate_decimated(twstft_plan* p, const int16_t* iq, size_t total_in
     p->be.free(d_wt);
     p->be.free(d_G);
     p->be.free(d_g);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Synthetic records on the device (bench / test tooling, k_synth.cuh)
+static inline uint64_t splitmix64(uint64_t& x)
+{
+    uint64_t z = (x += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static inline double unit(uint64_t& x) { return (double)(splitmix64(x) >> 11) * (1.0 / 9007199254740992.0); }
+
+static SynthLane synth_lane(uint64_t seed, int ch, i64 period, double delay, double df, double phase_cyc, double snr_db,
+                            double fs)
+{
+    SynthLane L{};
+    const double ps = pow(10.0, snr_db / 10.0);
+    const double sigma = 3000.0 / sqrt(1.0 + ps);            // per-component noise std: total I std ~ 3000 LSB
+    L.delay = ((i64)floor(delay) % period + period) % period;
+    L.dphi = df / fs;
+    L.phase = phase_cyc;
+    L.amp = (float)(sigma * sqrt(2.0 * ps));
+    L.sigma = (float)sigma;
+    L.dc_re = ch == 0 ? 11.3f : -5.2f;
+    L.dc_im = ch == 0 ? -7.9f : 3.4f;
+    uint64_t k = seed * 2 + (uint64_t)ch + 0x1234567ull;
+    const uint64_t kk = splitmix64(k);
+    L.key0 = (unsigned)kk;
+    L.key1 = (unsigned)(kk >> 32);
+    return L;
+}
+
+static int run_synth(twstft_plan* p, const std::vector<SynthLane>& lanes, int nch, i64 nsamp, short2* d_out)
+{
+    SynthLane* d_l = (SynthLane*)p->be.alloc(sizeof(SynthLane) * lanes.size());
+    if (!d_l || !p->be.ok()) return fail(p, TWSTFT_E_NOMEM, "device allocation failed");
+    p->be.h2d(d_l, lanes.data(), sizeof(SynthLane) * lanes.size());
+    SynthParams sp{};
+    sp.bits = p->d_bits; sp.period = (i64)p->code_nchips * p->cfg.samples_per_chip; sp.rep = p->cfg.samples_per_chip;
+    sp.nch = nch; sp.nsamp = nsamp; sp.lanes = d_l; sp.out = d_out;
+    i64 nblk = (nsamp + KSynth::NT - 1) / KSynth::NT;
+    const i64 cap = (i64)p->be.num_sms * 8;
+    if (nblk > cap) nblk = cap;
+    const size_t MAXY = 32768;
+    for (size_t l0 = 0; l0 < lanes.size(); l0 += MAXY) {           // gridDim.y limit
+        SynthParams q = sp;
+        q.lanes = d_l + l0;
+        q.out = d_out + (l0 / nch) * (size_t)nsamp * nch;
+        const size_t ny = std::min(MAXY, lanes.size() - l0);
+        p->be.launch<KSynth>(dim3((unsigned)nblk, (unsigned)ny, 1), q);
+    }
+    p->be.sync();
+    p->be.free(d_l);
+    return p->be.ok() ? TWSTFT_OK : fail(p, TWSTFT_E_CUDA, p->be.err_string());
+}
+
+int twstft_synth_records(twstft_plan* p, uint64_t seed0, size_t nrecords, double snr1_db, double snr2_db, int16_t* dev_out)
+{
+    if (!p || !p->pipe || !dev_out) return TWSTFT_E_ARG;
+    if (!p->have_code || p->code_qpsk) return fail(p, TWSTFT_E_NOCODE, "synthetic records need an installed BPSK code");
+    p->be.use();
+    const i64 N = p->cfg.nsamples;
+    std::vector<SynthLane> lanes(nrecords * p->nch);
+    for (size_t r = 0; r < nrecords; r++) {
+        uint64_t s = seed0 + r;
+        // ch1 delay 0.25..0.99 s, df +-9 kHz off grid, SNR -5 dB; ch2 loopback delay ~0.7253 s, df 0, +0.6 dB
+        const double d1 = (0.25 + 0.74 * unit(s)) * (double)N, f1 = (2.0 * unit(s) - 1.0) * 9000.0, p1 = unit(s);
+        const double d2 = 0.7253 * (double)N + (2.0 * unit(s) - 1.0), p2 = unit(s);
+        lanes[r * p->nch] = synth_lane(seed0 + r, 0, N, d1, f1, p1, snr1_db, p->cfg.fs);
+        if (p->nch == 2) lanes[r * 2 + 1] = synth_lane(seed0 + r, 1, N, d2, 0.0, p2, snr2_db, p->cfg.fs);
+    }
+    return run_synth(p, lanes, p->nch, N, reinterpret_cast<short2*>(dev_out));
+}
+
+int twstft_synth_stream(twstft_plan* p, uint64_t seed, size_t ninstants, double delay, double df, double snr_db,
+                        int16_t* dev_out)
+{
+    if (!p || !p->pipe || !dev_out || p->nch != 1) return TWSTFT_E_ARG;
+    if (!p->have_code || p->code_qpsk) return fail(p, TWSTFT_E_NOCODE, "synthetic records need an installed BPSK code");
+    p->be.use();
+    std::vector<SynthLane> lanes(1);
+    lanes[0] = synth_lane(seed, 0, (i64)p->code_nchips * p->cfg.samples_per_chip, delay, df, 0.3 / 6.283185307179586, snr_db, p->cfg.fs);
+    return run_synth(p, lanes, 1, (i64)ninstants, reinterpret_cast<short2*>(dev_out));
+}
+
+// ---------------------------------------------------------------------------------------------
+// A long run of records drawn cyclically from a pool (the day-of-data driver) and the multi-GPU sharder
+
+int twstft_process_cycled(twstft_plan* p, const int16_t* pool, int pool_on_device, size_t pool_records,
+                          size_t first_record, size_t nrecords, twstft_result* results)
+{
+    if (!p || !p->pipe || !pool || !results || pool_records == 0) return TWSTFT_E_ARG;
+    const size_t rec_i16 = p->raw_elems_per_rec * 2;
+    const size_t B = (size_t)p->cfg.max_batch;
+    for (size_t r = first_record; r < first_record + nrecords;) {
+        const size_t slot = r % pool_records;
+        size_t nb = std::min(B, pool_records - slot);
+        nb = std::min(nb, first_record + nrecords - r);
+        const int16_t* src = pool + slot * rec_i16;
+        twstft_result* out = results + (r - first_record) * p->nch;
+        const int rc = pool_on_device ? twstft_process_device(p, src, nb, out) : twstft_process(p, src, nb, out);
+        if (rc != TWSTFT_OK) return rc;
+        r += nb;
+    }
+    return TWSTFT_OK;
+}
+
+struct twstft_shard {
+    std::vector<twstft_plan*> plans;
+    std::vector<int> devices;
+    std::string err;
+};
+
+#ifndef TWSTFT_EMU
+// bind the calling thread to the CPUs the kernel lists as local to the GPU (sysfs), so that the pinned buffers it
+// allocates next are first-touched on that socket; a no-op when the topology is not exposed
+static void bind_thread_to_gpu(int device)
+{
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) return;
+    for (char* c = bus; *c; c++) *c = (char)tolower(*c);
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return;
+    char line[1024] = {0};
+    const bool got = fgets(line, sizeof line, f) != nullptr;
+    fclose(f);
+    if (!got) return;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int n = 0;
+    for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        const int k = sscanf(tok, "%d-%d", &a, &b);
+        if (k == 1) b = a;
+        if (k >= 1) for (int c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET(c, &set); n++; }
+    }
+    if (n > 0) sched_setaffinity(0, sizeof set, &set);
+}
+#else
+static void bind_thread_to_gpu(int) {}
+#endif
+
+int twstft_shard_create(const twstft_config* cfg, const int* devices, int ngpus, twstft_shard** out)
+{
+    if (!cfg || !out || ngpus < 1) return TWSTFT_E_ARG;
+    twstft_shard* s = new twstft_shard();
+    *out = s;
+    for (int g = 0; g < ngpus; g++) {
+        twstft_config c = *cfg;
+        c.device_id = devices ? devices[g] : g;
+        twstft_plan* p = nullptr;
+        const int rc = twstft_plan_create(&c, &p);
+        s->plans.push_back(p);
+        s->devices.push_back(c.device_id);
+        if (rc != TWSTFT_OK) { s->err = std::string("GPU ") + std::to_string(c.device_id) + ": " + twstft_last_error(p); return rc; }
+    }
+    return TWSTFT_OK;
+}
+void twstft_shard_destroy(twstft_shard* s)
+{
+    if (!s) return;
+    for (twstft_plan* p : s->plans) twstft_plan_destroy(p);
+    delete s;
+}
+int twstft_shard_ngpus(const twstft_shard* s) { return s ? (int)s->plans.size() : 0; }
+twstft_plan* twstft_shard_plan(twstft_shard* s, int g) { return (s && g >= 0 && g < (int)s->plans.size()) ? s->plans[g] : nullptr; }
+const char* twstft_shard_last_error(const twstft_shard* s) { return s ? s->err.c_str() : "null shard"; }
+
+int twstft_shard_set_code(twstft_shard* s, const uint8_t* chips, size_t nbytes, int qpsk)
+{
+    if (!s) return TWSTFT_E_ARG;
+    for (twstft_plan* p : s->plans) {
+        const int rc = twstft_set_code(p, chips, nbytes, qpsk);
+        if (rc != TWSTFT_OK) { s->err = twstft_last_error(p); return rc; }
+    }
+    return TWSTFT_OK;
+}
+
+}  // extern "C"
+// run fn(g) on one host thread per GPU; first error wins
+template <class F> static int shard_parallel(twstft_shard* s, F fn)
+{
+    const int G = (int)s->plans.size();
+    std::vector<int> rc(G, TWSTFT_OK);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; g++) th.emplace_back([&, g] { rc[g] = fn(g); });
+    for (auto& t : th) t.join();
+    for (int g = 0; g < G; g++)
+        if (rc[g] != TWSTFT_OK) { s->err = std::string("GPU ") + std::to_string(s->devices[g]) + ": " + twstft_last_error(s->plans[g]); return rc[g]; }
+    return TWSTFT_OK;
+}
+extern "C" {
+
+int twstft_shard_process(twstft_shard* s, const int16_t* iq, size_t nrecords, twstft_result* results)
+{
+    if (!s || !iq || !results) return TWSTFT_E_ARG;
+    const size_t G = s->plans.size();
+    return shard_parallel(s, [&](int g) {
+        twstft_plan* p = s->plans[g];
+        const size_t lo = nrecords * (size_t)g / G, hi = nrecords * (size_t)(g + 1) / G;      // SURVEY 8e record ranges
+        if (hi == lo) return (int)TWSTFT_OK;
+        bind_thread_to_gpu(s->devices[g]);
+        return twstft_process(p, iq + lo * p->raw_elems_per_rec * 2, hi - lo, results + lo * p->nch);
+    });
+}
+
+int twstft_shard_process_cycled(twstft_shard* s, const int16_t* pool, size_t pool_records, size_t nrecords, int resident,
+                                twstft_result* results, double* seconds_wall, double* seconds_dev)
+{
+    if (!s || !pool || !results || pool_records == 0) return TWSTFT_E_ARG;
+    const size_t G = s->plans.size();
+    std::vector<int16_t*> local(G, nullptr);       // per-GPU copy of the pool: device memory (resident) or pinned host memory
+    const size_t pool_bytes = pool_records * s->plans[0]->raw_elems_per_rec * sizeof(short2);
+    int rc = shard_parallel(s, [&](int g) {        // set-up, not timed
+        twstft_plan* p = s->plans[g];
+        bind_thread_to_gpu(s->devices[g]);
+        p->be.use();
+        if (resident) {
+            void* d = nullptr;
+            int r = twstft_device_alloc(p, pool_bytes, &d);
+            if (r != TWSTFT_OK) return r;
+            local[g] = (int16_t*)d;
+            return twstft_copy_to_device(p, d, pool, pool_bytes);
+        }
+        local[g] = (int16_t*)twstft_host_alloc(pool_bytes);       // first-touched by the thread bound to this GPU's CPUs
+        if (!local[g]) return fail(p, TWSTFT_E_NOMEM, "pinned host allocation failed");
+        memcpy(local[g], pool, pool_bytes);
+        return (int)TWSTFT_OK;
+    });
+    std::vector<float> dev_ms(G, 0.f);
+    const auto t0 = std::chrono::steady_clock::now();
+    if (rc == TWSTFT_OK)
+        rc = shard_parallel(s, [&](int g) {
+            twstft_plan* p = s->plans[g];
+            const size_t lo = nrecords * (size_t)g / G, hi = nrecords * (size_t)(g + 1) / G;
+            twstft_timer_start(p);
+            const int r = twstft_process_cycled(p, local[g], resident, pool_records, lo, hi - lo, results + lo * p->nch);
+            twstft_timer_stop(p, &dev_ms[g]);
+            return r;
+        });
+    const auto t1 = std::chrono::steady_clock::now();
+    if (seconds_wall) *seconds_wall = std::chrono::duration<double>(t1 - t0).count();
+    if (seconds_dev) for (size_t g = 0; g < G; g++) seconds_dev[g] = 1e-3 * dev_ms[g];
+    for (size_t g = 0; g < G; g++) {
+        if (!local[g]) continue;
+        if (resident) twstft_device_free(s->plans[g], local[g]);
+        else twstft_host_free(local[g]);
+    }
     return rc;
 }
 

@@ -10,9 +10,14 @@ fine delay / phase / SNR) over one batch of RECORDS_PER_STEP synthetic two-chann
   e2e    the same metric through twstft_process with HOST (pinned) records, H2D + D2H in the timed region
   roofline   dominant kernel: algorithmic bytes per launch / CUDA-event duration vs the measured HBM peak
   cpu_baseline  the numpy oracle (a port of godual_ranging.m) on one host core, one record
+  day    BASELINE configs[4]: 86 400 records drawn cyclically from a pool of DAY_POOL distinct records, sharded by
+         record range over the ranks, once from HBM-resident pools and once streamed from pinned host
+         memory; clocks and power sampled over the whole region; 32 random rows checked against the oracle
 --impl reference times the oracle port on all host cores (the reference's Octave/C++ cannot be built here).
+The synthetic records are generated on the device (twstft_synth_records: SURVEY 8d recipe, Philox noise).
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -29,6 +34,9 @@ N = 5000000
 FS = 5e6
 CODE = (22, 3, 2500000)          # bitlen, taps, noiselen (experiments/221207_twoway_codes/codes/noiselen2500000_bitlen22_taps03)
 RECORDS_PER_STEP = 32
+DAY_RECORDS = 86400
+DAY_POOL = 64                    # distinct records per rank the day is drawn from (record r = pool[r % DAY_POOL])
+SEED0 = 20261017
 METRIC = "two-channel 1-s 5 MS/s records correlated per second"
 UNIT = "records/s"
 SURVEY_BYTES_PER_RECORD = 1.4e9  # 140*N bytes per channel, two channels
@@ -56,11 +64,6 @@ def measured_peak():
         return 6650.0, "fallback"
 
 
-def make_records(code, seeds):
-    from amaranth_twstft_b200 import synth
-    return [synth.record_pair(code, s, fs=FS)[0] for s in seeds]
-
-
 class ClockSampler:
     """SM clock and clock-event (throttle) reasons sampled through NVML every millisecond by a thread, ONLY between
     begin() and end() -- i.e. during the timed region (B200_PROFILING.md clocks line; nvidia-smi -lms cannot sample a
@@ -68,7 +71,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.h, self.nv = index, None, None
-        self.sm, self.reasons, self.smax = [], set(), None
+        self.sm, self.pw, self.reasons, self.smax = [], [], set(), None
         self.on = threading.Event()
         self.quit = threading.Event()
         self.thread = None
@@ -92,6 +95,10 @@ class ClockSampler:
     def _sample(self):
         nv = self.nv
         self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            self.pw.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+        except Exception:
+            pass
         r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
         for name, bit in (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
                           ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
@@ -127,9 +134,15 @@ class ClockSampler:
             except Exception:
                 return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
         self.thread.join(timeout=1.0)
-        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax,
-                "reasons": sorted(self.reasons), "samples": len(self.sm),
-                "how": "NVML, 1 ms period, sampled only inside the timed region"}
+        return self.summary()
+
+    def summary(self, since=0):
+        sm, pw = self.sm[since:], self.pw[since:]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": float(min(sm)) if sm else None,
+                "sm_max_mhz": self.smax, "power_w_median": float(np.median(pw)) if pw else None,
+                "power_w_max": float(max(pw)) if pw else None,
+                "reasons": sorted(self.reasons), "samples": len(sm),
+                "how": "NVML, 1 ms period, sampled only inside the timed regions"}
 
 
 def bind_to_gpu_numa(index):
@@ -160,7 +173,15 @@ def oracle_record(raw, code):
     return oc.record_G(raw, k, freq, oc.fcode_G(code), code, fs=FS)
 
 
-def _ref_worker(args):
+def _json_default(o):
+    return o.item() if hasattr(o, "item") else str(o)
+
+
+_REF = {}
+
+
+def _ref_prepare(args):
+    """Untimed: every worker builds its record, code spectrum and axis once."""
     seed, = args
     from oracle import correlator as oc
     from oracle import prn
@@ -168,10 +189,15 @@ def _ref_worker(args):
     code = oc.code_bpsk(prn.lfsr_bits(*CODE))
     raw, _ = synth.record_pair(code, seed, fs=FS)
     freq = oc.freq_axis_G(FS, N)
-    k = oc.window(freq, -20000.0, 20000.0)
-    fcode = oc.fcode_G(code)
+    _REF.update(code=code, raw=raw, freq=freq, k=oc.window(freq, -20000.0, 20000.0), fcode=oc.fcode_G(code))
+    return os.getpid()
+
+
+def _ref_worker(_):
+    """Timed: ONE channel-correlation (half a record) through the oracle port of godual_ranging.m."""
+    from oracle import correlator as oc
     t0 = time.perf_counter()
-    oc.record_G(raw, k, freq, fcode, code, fs=FS, channels=(1,))     # ONE channel = half a record
+    oc.record_G(_REF["raw"], _REF["k"], _REF["freq"], _REF["fcode"], _REF["code"], fs=FS, channels=(1,))
     return time.perf_counter() - t0
 
 
@@ -187,9 +213,10 @@ def run_reference(args):
     ctx = mp.get_context("fork")
     times = []
     with ctx.Pool(workers) as pool:
+        pool.map(_ref_prepare, [(SEED0 + i,) for i in range(workers)], chunksize=1)     # inputs resident before timing
         for step in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            pool.map(_ref_worker, [(20261017 + step * workers + i,) for i in range(workers)])
+            pool.map(_ref_worker, range(workers), chunksize=1)
             dt = time.perf_counter() - t0
             if step >= args.warmup:
                 times.append(dt)
@@ -204,7 +231,83 @@ def run_reference(args):
                              "sample": f"{workers} single-channel correlations (half records) per step, numpy oracle "
                                        "port of processing/Octave/godual_ranging.m, one process per core"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line, default=_json_default), flush=True)
+
+
+def _spot_worker(args):
+    raw, chan = args
+    from oracle import correlator as oc
+    from oracle import prn
+    code = oc.code_bpsk(prn.lfsr_bits(*CODE))
+    freq = oc.freq_axis_G(FS, N)
+    o = oc.record_G(raw, oc.window(freq, -20000.0, 20000.0), freq, oc.fcode_G(code), code, fs=FS, channels=(chan,))[chan]
+    return {k: (complex(o[k]) if k == "xval" else float(o[k])) for k in ("indice", "correction", "xval", "SNRr", "SNRi", "df")}
+
+
+def run_day(cor, args, rank, world, dev, host, P, rec_bytes, code, sampler, barrier, max_over_ranks):
+    """BASELINE configs[4]: a day of 86 400 two-channel records, record r drawn from pool slot r % P, the rank's share
+    [rank*D/world, (rank+1)*D/world); no collective on the data path.  Resident: pool in HBM.  Streamed:
+    every record copied from pinned host memory (double-buffered inside twstft_process).  Device time = CUDA events on
+    the plan's stream, max over ranks; the host wall clock of the same region is reported beside it."""
+    out = {"records": args.day_records, "pool_records_per_rank": P, "sharding": "record ranges, one rank per GPU, "
+           "no collective; rows gathered on the host", "legs": {}}
+    rows_res = None
+    for leg, nday, src, on_dev in (("resident", args.day_records, dev, True),
+                                   ("streamed", min(args.day_streamed_records, args.day_records), host, False)):
+        if nday <= 0:
+            continue
+        lo, hi = nday * rank // world, nday * (rank + 1) // world
+        cor.process_cycled(src, P, lo, min(2 * int(cor.cfg.max_batch), hi - lo), on_device=on_dev)    # warm-up
+        cor.synchronize()
+        f0 = cor.fast_counters
+        barrier()
+        mark = len(sampler.sm)
+        sampler.begin()
+        t0 = time.perf_counter()
+        cor.timer_start()
+        rows = cor.process_cycled(src, P, lo, hi - lo, on_device=on_dev)
+        ms = cor.timer_stop()
+        wall = time.perf_counter() - t0
+        sampler.end()
+        barrier()
+        ms = max_over_ranks(ms)
+        wall = max_over_ranks(wall)
+        f1 = cor.fast_counters
+        entry = {"records": nday, "seconds_device": ms * 1e-3, "seconds_wall": wall, "records_per_s": nday / (ms * 1e-3),
+                 "rank0_fast_peak": {"records": f1[0] - f0[0], "rerun_in_full": f1[1] - f0[1]},
+                 "clocks": sampler.summary(mark)}
+        if nday < args.day_records:
+            entry["seconds_for_a_day_extrapolated"] = ms * 1e-3 * args.day_records / nday
+        out["legs"][leg] = entry
+        if leg == "resident":
+            rows_res, lo_res = rows, lo
+        else:   # the two legs draw the same records: rows must agree bit for bit wherever both ran
+            m = min(len(rows), len(rows_res)) if lo == lo_res else 0
+            entry["rows_equal_resident_leg"] = bool(m and np.array_equal(rows[:m], rows_res[:m]))
+    if rank == 0 and rows_res is not None and not args.no_cpu_baseline:
+        # parity spot check: 32 random rows of rank 0's share against the oracle, on the host copy of the pool record
+        import multiprocessing as mp
+        rng = np.random.default_rng(SEED0)
+        picks = [(int(rng.integers(0, len(rows_res))), int(rng.integers(1, 3))) for _ in range(32)]
+        per = rec_bytes // 2
+        jobs = [(np.array(host[((lo_res + r) % P) * per:((lo_res + r) % P + 1) * per]), ch) for r, ch in picks]
+        t0 = time.perf_counter()
+        with mp.get_context("fork").Pool(min(16, os.cpu_count() or 1)) as pool:
+            refs = pool.map(_spot_worker, jobs, chunksize=1)
+        worst = {"index_mismatches": 0, "fine_delay_samples": 0.0, "phase_rad": 0.0, "snr_db": 0.0, "df_mismatches": 0}
+        for (r, ch), o in zip(picks, refs):
+            g = rows_res[r, ch - 1]
+            worst["index_mismatches"] += int(g["indice"]) != int(o["indice"])
+            worst["df_mismatches"] += g["df"] != o["df"]
+            worst["fine_delay_samples"] = max(worst["fine_delay_samples"], abs(g["correction"] - o["correction"]) / 3.0)
+            worst["phase_rad"] = max(worst["phase_rad"], abs(np.angle(complex(g["xval_re"], g["xval_im"]) * np.conj(o["xval"]))))
+            worst["snr_db"] = max(worst["snr_db"], abs(10 * np.log10(g["SNRr"] + g["SNRi"]) - 10 * np.log10(o["SNRr"] + o["SNRi"])))
+        ok = (worst["index_mismatches"] == 0 and worst["df_mismatches"] == 0 and worst["fine_delay_samples"] < 1e-4
+              and worst["phase_rad"] < 1e-4 and worst["snr_db"] < 0.01)
+        out["parity_spot_check"] = {"rows": len(picks), "ok": bool(ok), "worst": worst,
+                                    "tolerances": {"index": "exact", "fine_delay_samples": 1e-4, "phase_rad": 1e-4, "snr_db": 0.01},
+                                    "oracle_seconds": time.perf_counter() - t0}
+    return out
 
 
 def main():
@@ -215,6 +318,10 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--records-per-step", type=int, default=RECORDS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-day", action="store_true", help="skip the 86 400-record day leg")
+    ap.add_argument("--day-records", type=int, default=DAY_RECORDS)
+    ap.add_argument("--day-streamed-records", type=int, default=DAY_RECORDS,
+                    help="records of the streamed (host-fed) day leg; the resident leg always runs --day-records")
     ap.add_argument("--no-fast-peak", action="store_true",
                     help="three-polyphase inverse for every record instead of the certified one-transform peak path")
     args = ap.parse_args()
@@ -254,14 +361,15 @@ def main():
     assert cor.backend == "cuda"
     bits = cor.gen_code(CODE[0], CODE[1])
     code = 2.0 * np.repeat(bits.astype(np.float64), 2) - 1.0
-    # resident pool: R distinct records per rank (R*40 MB >> 126 MB L2 for R >= 4)
-    recs = make_records(code, [20261017 + rank * 1000 + i for i in range(R)])
-    rec_bytes = recs[0].nbytes
-    pinned = cor.pinned_empty(R * rec_bytes)
+    # resident pool: P >= R distinct records per rank, generated on the device (R*40 MB >> 126 MB L2 for R >= 4);
+    # a pinned host copy of it feeds the end-to-end and streamed legs
+    P = max(R, DAY_POOL if not args.no_day else R)
+    rec_bytes = 4 * N * 2                          # [I1 Q1 I2 Q2] int16 per sample instant: 40 MB per record
+    dev = cor.synth_records(SEED0 + rank * 100000, P)
+    pinned = cor.pinned_empty(P * rec_bytes)
     host = pinned.view(np.int16)
-    for i, r in enumerate(recs):
-        host[i * r.size:(i + 1) * r.size] = r
-    dev = cor.to_device(host)
+    cor._check(cor.lib.twstft_copy_to_host(cor._plan, host.ctypes.data, dev, P * rec_bytes), "twstft_copy_to_host")
+    recs = [host[:rec_bytes // 2]]                 # record 0 of this rank, for the CPU baseline leg
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -282,18 +390,38 @@ def main():
     value = world * R * args.steps / (ms * 1e-3)
 
     # end to end: host (pinned) records in, results out, copies inside the timed region
+    host_r = host[:R * rec_bytes // 2]
     for _ in range(2):
-        cor.process(host)
+        cor.process(host_r)
     barrier()
     sampler.begin()
     cor.timer_start()
     e2e_steps = max(3, args.steps // 2)
     for _ in range(e2e_steps):
-        res_e2e = cor.process(host)
+        res_e2e = cor.process(host_r)
     ms_e2e = max_over_ranks(cor.timer_stop())
-    clocks = sampler.stop()
+    sampler.end()
     e2e_value = world * R * e2e_steps / (ms_e2e * 1e-3)
     barrier()
+
+    # host->device ceiling of THIS box at THIS GPU count: the same pinned records copied with nothing else running,
+    # all ranks at once (what bounds the end-to-end rate: 40 MB per record over PCIe / host memory)
+    scratch = C.c_void_p()
+    cor._check(cor.lib.twstft_device_alloc(cor._plan, R * rec_bytes, C.byref(scratch)), "twstft_device_alloc")
+    for rep in range(2):
+        barrier()
+        cor.timer_start()
+        for _ in range(4 if rep else 1):
+            cor.lib.twstft_copy_to_device(cor._plan, scratch, host_r.ctypes.data, R * rec_bytes)
+        ms_h2d = max_over_ranks(cor.timer_stop())
+    cor.device_free(scratch)
+    h2d_gbs = world * 4 * R * rec_bytes / (ms_h2d * 1e-3) / 1e9
+    barrier()
+
+    day = None
+    if not args.no_day:
+        day = run_day(cor, args, rank, world, dev, host, P, rec_bytes, code, sampler, barrier, max_over_ranks)
+    clocks = sampler.stop()
 
     # per-kernel durations (CUDA events around every launch, two extra steps)
     cor.profile(True)
@@ -309,7 +437,7 @@ def main():
         if name in alg_n or name in moved_n:
             # bytes the kernel has to move for the algorithm it executes -> achieved GB/s
             b = moved_n.get(name, 0) * N * 2 * R
-            ent["alg_bytes"] = b
+            ent["moved_bytes"] = b
             ent["gbs"] = b / (avg * 1e-3) / 1e9
             ent["frac"] = ent["gbs"] / peak
             # the share of SURVEY 8d's 140N budget that this kernel's job stands for (fusion / the fast peak path
@@ -321,7 +449,7 @@ def main():
     tot = sum(v[0] for v in prof.values()) or 1.0
     for name in kernels:
         kernels[name]["share"] = prof[name][0] / tot
-    dom = max((k for k in kernels if kernels[k].get("alg_bytes")), key=lambda k: prof[k][0], default=None)
+    dom = max((k for k in kernels if kernels[k].get("moved_bytes")), key=lambda k: prof[k][0], default=None)
     roofline = None
     if dom:
         traffic = None          # dram bytes per launch from the committed ncu --set full capture (profiles/)
@@ -333,7 +461,7 @@ def main():
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
                     "frac": kernels[dom]["frac"], "traffic": traffic, "peak_kind": peak_kind,
                     "share_of_step": kernels[dom]["share"],
-                    "alg_bytes_per_launch": kernels[dom]["alg_bytes"],
+                    "moved_bytes_per_launch": kernels[dom]["moved_bytes"],
                     "survey_budget_bytes_per_launch": kernels[dom]["survey_budget_bytes"],
                     "frac_survey_budget": kernels[dom]["frac_survey_budget"],
                     "pipeline_survey_formula": {"achieved": value / world * SURVEY_BYTES_PER_RECORD / 1e9,
@@ -355,7 +483,12 @@ def main():
             "clocks": clocks, "gpu_launches": launches,
             "fast_peak": dict(zip(("records", "rerun_in_full"), cor.fast_counters)) if fast else None,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": R * rec_bytes,
-                    "d2h_bytes_per_step": int(res_e2e.nbytes)},
+                    "d2h_bytes_per_step": int(res_e2e.nbytes),
+                    "h2d_ceiling_gbs": h2d_gbs, "h2d_achieved_gbs": e2e_value * rec_bytes / 1e9,
+                    "frac_of_h2d_ceiling": e2e_value * rec_bytes / 1e9 / h2d_gbs,
+                    "note": "h2d_ceiling = the same pinned records copied host->device with nothing else running, "
+                            "all ranks at once on this box: the bound of the end-to-end rate"},
+            "day": day,
             "roofline": roofline, "kernels": kernels,
             "pipeline": {"moved_bytes_per_record": moved_total_n * N * 2,
                          "frac_of_hbm_peak_bytes_moved": value / world * moved_total_n * N * 2 / 1e9 / peak,
@@ -373,7 +506,7 @@ def main():
                                           "port of processing/Octave/godual_ranging.m, single process",
                                 "parity_with_gpu_on_sample": "ok" if ok else "MISMATCH"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line, default=_json_default), flush=True)
     cor.device_free(dev)
     cor.close()
     if dist is not None:

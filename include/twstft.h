@@ -219,6 +219,40 @@ int twstft_estimate_carrier_block(twstft_plan* plan, const int16_t* iq, int iq_o
 int twstft_estimate_decimated(twstft_plan* plan, const int16_t* iq, size_t total_instants, int dec, double foffset,
                               int remote, double* df, int64_t* pos);
 
+/* ---- multi-GPU: records are independent (godual_ranging.m:75-102 keeps no state between records), so
+ * a run of records is split by index, GPU g of G taking [g*R/G, (g+1)*R/G): one host thread + one plan per GPU, the
+ * code spectrum replicated, rows written at their record index of the caller's array.  No collective, no NCCL. ---- */
+typedef struct twstft_shard twstft_shard;
+int twstft_shard_create(const twstft_config* cfg, const int* devices /* NULL: 0..ngpus-1 */, int ngpus, twstft_shard** out);
+void twstft_shard_destroy(twstft_shard* s);
+int twstft_shard_ngpus(const twstft_shard* s);
+twstft_plan* twstft_shard_plan(twstft_shard* s, int g);          /* e.g. to twstft_gen_code on plan 0 and read the chips */
+const char* twstft_shard_last_error(const twstft_shard* s);
+int twstft_shard_set_code(twstft_shard* s, const uint8_t* chips, size_t nbytes, int qpsk);
+/* the record loop of godual_ranging.m:75-102 / processing/CPP/main.cpp:452-519 over nrecords HOST records */
+int twstft_shard_process(twstft_shard* s, const int16_t* iq, size_t nrecords, twstft_result* results);
+/* One plan: nrecords records first_record.. drawn cyclically from a pool (record r = pool[r % pool_records]), pool in
+ * host or device memory.  The day-of-data driver (BASELINE configs[4]) when a day does not fit host memory. */
+int twstft_process_cycled(twstft_plan* plan, const int16_t* pool, int pool_on_device, size_t pool_records,
+                          size_t first_record, size_t nrecords, twstft_result* results);
+/* The same over all GPUs of a shard.  resident != 0: every GPU first uploads the pool (untimed) and correlates from
+ * HBM; 0: every record is streamed from a per-GPU pinned copy of the pool allocated by the thread bound to that GPU's
+ * CPUs.  seconds_wall: host wall clock of the parallel region; seconds_dev[g]: CUDA-event time on GPU g's stream. */
+int twstft_shard_process_cycled(twstft_shard* s, const int16_t* pool, size_t pool_records, size_t nrecords, int resident,
+                                twstft_result* results, double* seconds_wall, double* seconds_dev);
+
+/* ---- synthetic inputs generated on the device (bench / test tooling; SURVEY.md 8d recipe: delayed code * carrier
+ * + AWGN at a chosen SNR, round + saturate to int16; Philox noise keyed by the record seed). ----
+ * twstft_synth_records: nrecords records in the plan's layout into DEVICE memory; record r uses seed0 + r; channel 1
+ *   delay 0.25..0.99 of the window, df +-9 kHz, SNR snr1_db; channel 2 (two-channel layout) the loopback: delay
+ *   ~0.7253 of the window, df 0, SNR snr2_db.
+ * twstft_synth_stream: one single-channel recording of ninstants sample instants, the installed code repeating back
+ *   to back (rx_multi_samples.cpp:214-215 files of the K scripts). */
+int twstft_synth_records(twstft_plan* plan, uint64_t seed0, size_t nrecords, double snr1_db, double snr2_db,
+                         int16_t* dev_out);
+int twstft_synth_stream(twstft_plan* plan, uint64_t seed, size_t ninstants, double delay, double df, double snr_db,
+                        int16_t* dev_out);
+
 /* Pinned host memory for the end-to-end path, device memory helpers for device-resident inputs. */
 void* twstft_host_alloc(size_t bytes);
 void twstft_host_free(void* p);
