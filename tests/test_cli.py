@@ -19,14 +19,14 @@ N = 10000
 
 def _build(libdir, libname, out):
     subprocess.check_call(["gcc", "-O2", "-std=c11", "-o", out, os.path.join(CDIR, "godual.c"), f"-L{libdir}",
-                           f"-l{libname}", f"-Wl,-rpath,{libdir}", "-lm"])
+                           f"-l{libname}", f"-Wl,-rpath,{libdir}", "-lm", "-lpthread"])
     return out
 
 
-def _run_cli(exe, tmp_path, lib, remote=0):
+def _run_cli(exe, tmp_path, lib, remote=0, nrec=3, gpus=None):
     bits, code = pc.make_code(N)
     kw = dict(ch1=dict(df=51234.5)) if remote else {}
-    recs = [synth.record_pair(code, 700 + i, **kw)[0] for i in range(3)]
+    recs = [synth.record_pair(code, 700 + i, **kw)[0] for i in range(nrec)]
     data = tmp_path / "1671606372short.bin"
     with open(data, "wb") as f:
         for r in recs:
@@ -34,9 +34,11 @@ def _run_cli(exe, tmp_path, lib, remote=0):
         f.write(recs[0][:1000].tobytes())          # trailing partial record: ignored (godual_ranging.m:81,102)
     codef = tmp_path / "code.bin"
     codef.write_bytes(bits.tobytes())
-    out = subprocess.run([exe, str(data), str(codef), str(remote), "2"], capture_output=True, text=True, check=True)
+    out = subprocess.run([exe, str(data), str(codef), str(remote), "2"] + ([str(gpus)] if gpus else []),
+                         capture_output=True, text=True, check=True)
     rows = [ln.split("\t") for ln in out.stdout.replace("\r", "").strip().splitlines()]
-    assert len(rows) == 3 and all(len(r) == (5 if remote else 9) for r in rows)
+    assert len(rows) == nrec and all(len(r) == (5 if remote else 9) for r in rows)
+    assert f"{nrec} records in" in out.stderr and "records/s" in out.stderr          # file -> rows throughput line
     mat = scipy.io.loadmat(str(tmp_path / (("remote" if remote else "") + "1671606372short.mat")))
     win = (80000.0, 120000.0) if remote else (-20000.0, 20000.0)
     with Correlator(nsamples=N, window_hz=win, max_batch=2, lib=lib, fast_peak=True) as cor:   # like godual.c
@@ -47,7 +49,7 @@ def _run_cli(exe, tmp_path, lib, remote=0):
                            ("df", "df"), ("puissance", "puissance"), ("puissance%dcode", "puissancecode"),
                            ("puissance%dnoise", "puissancenoise")):
             name = var % ch if "%d" in var else f"{var}{ch}"
-            assert mat[name].shape == (1, 3), name
+            assert mat[name].shape == (1, nrec), name
             assert np.array_equal(mat[name][0], ref[field][:, ch - 1]), name
     if remote:
         assert "indice2" not in mat
@@ -67,6 +69,14 @@ def _run_cli(exe, tmp_path, lib, remote=0):
 def test_godual_cli_emulation(tmp_path, remote):
     exe = _build(os.path.dirname(pc.EMU_LIB), "twstft_emu", str(tmp_path / "godual_emu"))
     _run_cli(exe, tmp_path, pc.EMU_LIB, remote)
+
+
+@pytest.mark.skipif(not os.path.exists(pc.EMU_LIB), reason="emulation library not built")
+def test_godual_cli_sharded_with_overlapped_ingest(tmp_path):
+    """Seven records, chunks of batch*gpus = 4 through two plans: the reader thread refills a slot while the other is
+    processed, rows stay in file order, the short last chunk and the trailing partial record end the loop."""
+    exe = _build(os.path.dirname(pc.EMU_LIB), "twstft_emu", str(tmp_path / "godual_emu"))
+    _run_cli(exe, tmp_path, pc.EMU_LIB, 0, nrec=7, gpus=2)
 
 
 @pytest.mark.gpu
