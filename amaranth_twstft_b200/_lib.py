@@ -26,7 +26,7 @@ EXPORTS = [
     "twstft_search_df_block", "twstft_estimate_decimated", "twstft_processing_cf64", "twstft_processing_cf64_df",
     "twstft_search_df_cf64", "twstft_shard_create", "twstft_shard_destroy", "twstft_shard_ngpus", "twstft_shard_plan",
     "twstft_shard_last_error", "twstft_shard_set_code", "twstft_shard_process", "twstft_process_cycled",
-    "twstft_shard_process_cycled", "twstft_synth_records", "twstft_synth_stream", "twstft_fast_counters", "twstft_timer_start", "twstft_timer_stop", "twstft_profile_enable", "twstft_profile_read",
+    "twstft_shard_process_cycled", "twstft_synth_records", "twstft_synth_stream", "twstft_fast_suspended", "twstft_fast_counters", "twstft_timer_start", "twstft_timer_stop", "twstft_profile_enable", "twstft_profile_read",
 ]
 
 
@@ -107,6 +107,8 @@ def load(path=None):
     lib.twstft_synth_stream.argtypes = [P, C.c_uint64, C.c_size_t, C.c_double, C.c_double, C.c_double, P]
     lib.twstft_estimate_bins.argtypes = [P, P, C.c_int, C.c_size_t, C.c_int64, C.c_int, P]
     lib.twstft_fast_counters.argtypes = [P, P, P]
+    lib.twstft_fast_suspended.argtypes = [P]
+    lib.twstft_fast_suspended.restype = C.c_int64
     lib.twstft_estimate_decimated.argtypes = [P, P, C.c_size_t, C.c_int, C.c_double, C.c_int, P, P]
     lib.twstft_host_alloc.argtypes = [C.c_size_t]
     lib.twstft_host_alloc.restype = P

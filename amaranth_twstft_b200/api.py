@@ -108,6 +108,11 @@ class Correlator:
         self.lib.twstft_fast_counters(self._plan, C.byref(a), C.byref(b))
         return a.value, b.value
 
+    @property
+    def fast_suspended(self):
+        """Records that went through the full path because the fast path's fall-back rate made it a loss."""
+        return int(self.lib.twstft_fast_suspended(self._plan))
+
     def window_bins(self):
         lo, hi = C.c_int64(), C.c_int64()
         self.lib.twstft_window_bins(self._plan, C.byref(lo), C.byref(hi))

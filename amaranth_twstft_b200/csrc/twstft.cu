@@ -38,6 +38,14 @@ struct twstft_plan {
     unsigned char* d_bits = nullptr;
     size_t bits_cap = 0;
     long long fast_records = 0, fast_rerun = 0;   // records through the fast peak path / re-run through the full path
+    // governor of the fast peak path: an uncertified record costs a fast attempt PLUS the full path, so the path only
+    // pays while less than about a quarter of the records fall back.  Over every window of FAST_WIN records the
+    // fall-back rate is measured; above FAST_MAX_RATE the plan runs the full path for the next FAST_OFF records and
+    // then probes again.  Results are identical either way.
+    long long fast_win_seen = 0, fast_win_rerun = 0, fast_off_left = 0, fast_suspended = 0;
+    long long fast_win = 64, fast_off = 1024;     // TWSTFT_FAST_WIN / TWSTFT_FAST_OFF override them (tests)
+    short2* d_winbuf = nullptr;    // staging of twstft_process_windows' host buffers (grows, never shrinks)
+    size_t win_cap = 0;
     double2* d_cf64 = nullptr;     // upload staging of the complex-double entry points (one chunk)
     float2* d_cf32 = nullptr;      // their windows as complex float
     size_t cf64_cap = 0, cf32_cap = 0;   // samples
@@ -120,6 +128,8 @@ int twstft_plan_create(const twstft_config* cfg, twstft_plan** out)
     p->max_lanes = cfg->max_batch * p->nch;
     if (p->pipe->setup(&p->be, p->max_lanes, p->nq) != 0)
         return fail(p, TWSTFT_E_NOMEM, std::string("device allocation failed: ") + p->be.err_string());
+    if (const char* e = getenv("TWSTFT_FAST_WIN")) { if (atoll(e) > 0) p->fast_win = atoll(e); }
+    if (const char* e = getenv("TWSTFT_FAST_OFF")) { if (atoll(e) > 0) p->fast_off = atoll(e); }
     if (cfg->fast_peak && p->pipe->set_fast_peak(1) != 0)
         return fail(p, TWSTFT_E_NOMEM, std::string("device allocation failed (fast peak path): ") + p->be.err_string());
     const i64 N = cfg->nsamples;
@@ -159,6 +169,7 @@ void twstft_plan_destroy(twstft_plan* p)
     p->be.free(p->d_bits);
     p->be.free(p->d_cf64);
     p->be.free(p->d_cf32);
+    p->be.free(p->d_winbuf);
     p->be.shutdown();
     delete p;
 }
@@ -172,6 +183,8 @@ int twstft_fast_counters(const twstft_plan* p, int64_t* records, int64_t* rerun)
     if (rerun) *rerun = p->fast_rerun;
     return TWSTFT_OK;
 }
+
+int64_t twstft_fast_suspended(const twstft_plan* p) { return p ? p->fast_suspended : 0; }
 
 int64_t twstft_kernel_launches(const twstft_plan* p) { return p ? p->be.launches : 0; }
 
@@ -305,31 +318,66 @@ static int ensure_raw(twstft_plan* p)
     return (p->d_raw && p->be.ok()) ? 0 : -1;
 }
 
-// Fast peak path (k_fast.cuh): rows whose certificate failed carry status bit 2; those records go through the full
-// three-polyphase path here, one at a time (rare: records without a correlation peak).  `src` host or device.
-static int rerun_uncertified(twstft_plan* p, const short2* src, bool on_device, size_t nrecords, twstft_result* results)
+static constexpr double FAST_MAX_RATE = 0.25;
+
+static bool fast_on(const twstft_plan* p) { return p->cfg.fast_peak && p->fast_off_left <= 0; }
+
+static void fast_account(twstft_plan* p, size_t n, size_t nrerun, bool was_fast)
 {
-    p->fast_records += (long long)nrecords;
+    if (!p->cfg.fast_peak) return;
+    if (!was_fast) { p->fast_off_left -= (long long)n; p->fast_suspended += (long long)n; return; }
+    p->fast_records += (long long)n;
+    p->fast_rerun += (long long)nrerun;
+    p->fast_win_seen += (long long)n;
+    p->fast_win_rerun += (long long)nrerun;
+    if (p->fast_win_seen >= p->fast_win) {
+        if ((double)p->fast_win_rerun > FAST_MAX_RATE * (double)p->fast_win_seen) p->fast_off_left = p->fast_off;
+        p->fast_win_seen = p->fast_win_rerun = 0;
+    }
+}
+
+// Fast peak path (k_fast.cuh): rows whose certificate failed carry status bit 2; those records go through the full
+// three-polyphase path here, ALL FLAGGED RECORDS OF THE CALL IN BATCHES (one launch sequence per max_batch of them,
+// addressed through the window-offset table when they sit in device memory, copied into the staging slots when they
+// sit in host memory).  `src` host or device; returns the number of re-run records through *nrerun.
+static int rerun_uncertified(twstft_plan* p, const short2* src, bool on_device, size_t nrecords, twstft_result* results,
+                             size_t* nrerun)
+{
+    std::vector<size_t> flagged;
     for (size_t r = 0; r < nrecords; r++) {
-        bool flagged = false;
-        for (int c = 0; c < p->nch; c++) flagged = flagged || (((int)results[r * p->nch + c].status) & 4);
-        if (!flagged) continue;
-        p->fast_rerun++;
-        const short2* d = src + r * p->raw_elems_per_rec;
-        if (!on_device) {
-            p->be.h2d(p->d_raw, d, sizeof(short2) * p->raw_elems_per_rec);
-            d = p->d_raw;
-        }
+        bool f = false;
+        for (int c = 0; c < p->nch; c++) f = f || (((int)results[r * p->nch + c].status) & 4);
+        if (f) flagged.push_back(r);
+    }
+    if (nrerun) *nrerun = flagged.size();
+    const size_t B = (size_t)p->cfg.max_batch;
+    std::vector<i64> off(B);
+    std::vector<twstft_result> rows(B * p->nch);
+    for (size_t f0 = 0; f0 < flagged.size(); f0 += B) {
+        const int nb = (int)std::min(B, flagged.size() - f0);
         RunArgs a{};
-        a.d_raw = d; a.nrec = 1; a.nch = p->nch; a.rec_stride = (i64)p->raw_elems_per_rec; a.d_rec_offset = nullptr;
+        if (on_device) {
+            for (int i = 0; i < nb; i++) off[i] = (i64)(flagged[f0 + i] * p->raw_elems_per_rec);
+            p->be.h2d(p->d_off, off.data(), sizeof(i64) * nb);
+            a.d_raw = src; a.rec_stride = 0; a.d_rec_offset = p->d_off;
+        } else {
+            if (ensure_raw(p) != 0) return fail(p, TWSTFT_E_NOMEM, "device allocation failed");
+            for (int i = 0; i < nb; i++)
+                p->be.h2d(p->d_raw + (size_t)i * p->raw_elems_per_rec, src + flagged[f0 + i] * p->raw_elems_per_rec,
+                          sizeof(short2) * p->raw_elems_per_rec);
+            a.d_raw = p->d_raw; a.rec_stride = (i64)p->raw_elems_per_rec; a.d_rec_offset = nullptr;
+        }
+        a.nrec = nb; a.nch = p->nch;
         a.estimate = 1; a.variant = p->cfg.variant; a.ddof = p->cfg.ddof; a.fs = p->cfg.fs; a.d_out = p->d_res;
         a.allow_fast = 0;
         if (p->pipe->estimate(a, p->est) != 0) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
         if (p->cfg.fine_freq && p->pipe->fine_frequency(a) != 0) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
         if (p->pipe->correlate(a) != 0) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
-        p->be.d2h(results + r * p->nch, p->d_res, sizeof(Result) * p->nch);
+        p->be.d2h(rows.data(), p->d_res, sizeof(Result) * nb * p->nch);
         p->be.sync();
         if (!p->be.ok()) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
+        for (int i = 0; i < nb; i++)
+            memcpy(results + flagged[f0 + i] * p->nch, rows.data() + (size_t)i * p->nch, sizeof(twstft_result) * p->nch);
     }
     return TWSTFT_OK;
 }
@@ -338,13 +386,14 @@ static int rerun_uncertified(twstft_plan* p, const short2* src, bool on_device, 
 static int process_dev(twstft_plan* p, const short2* d_iq, size_t nrecords, twstft_result* results)
 {
     const int B = p->cfg.max_batch;
+    const bool fast = fast_on(p);
     for (size_t r0 = 0; r0 < nrecords; r0 += B) {
         const int nb = (int)((nrecords - r0) < (size_t)B ? (nrecords - r0) : B);
         RunArgs a{};
         a.d_raw = d_iq + r0 * p->raw_elems_per_rec;
         a.nrec = nb; a.nch = p->nch; a.rec_stride = (i64)p->raw_elems_per_rec; a.d_rec_offset = nullptr;
         a.estimate = 1; a.variant = p->cfg.variant; a.ddof = p->cfg.ddof; a.fs = p->cfg.fs; a.d_out = p->d_res;
-        a.allow_fast = p->cfg.fast_peak;
+        a.allow_fast = fast;
         if (p->pipe->estimate(a, p->est) != 0) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
         if (p->cfg.fine_freq) {
             const int frc = p->pipe->fine_frequency(a);
@@ -357,7 +406,12 @@ static int process_dev(twstft_plan* p, const short2* d_iq, size_t nrecords, twst
         p->be.sync();
         if (!p->be.ok()) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
     }
-    if (p->cfg.fast_peak) return rerun_uncertified(p, d_iq, true, nrecords, results);
+    size_t nrerun = 0;
+    if (fast) {
+        const int rc = rerun_uncertified(p, d_iq, true, nrecords, results, &nrerun);
+        if (rc != TWSTFT_OK) return rc;
+    }
+    fast_account(p, nrecords, nrerun, fast);
     return TWSTFT_OK;
 }
 
@@ -390,6 +444,7 @@ int twstft_process(twstft_plan* p, const int16_t* iq, size_t nrecords, twstft_re
     if (ensure_raw(p) != 0 || ensure_results(p, nrecords * p->nch) != 0)
         return fail(p, TWSTFT_E_NOMEM, "device allocation failed");
     const size_t B = (size_t)p->cfg.max_batch;
+    const bool fast = fast_on(p);
     // One record per chunk: the copy of a record (0.72 ms at 55 GB/s) hides the kernels of the previous one
     // (0.33 ms), so the only time not covered by the PCIe transfer is the last chunk's compute -- keep it small.
     const size_t chunk = 1;
@@ -403,7 +458,7 @@ int twstft_process(twstft_plan* p, const int16_t* iq, size_t nrecords, twstft_re
         a.d_raw = d; a.nrec = (int)nb; a.nch = p->nch; a.rec_stride = (i64)p->raw_elems_per_rec; a.d_rec_offset = nullptr;
         a.estimate = 1; a.variant = p->cfg.variant; a.ddof = p->cfg.ddof; a.fs = p->cfg.fs;
         a.d_out = p->d_res + r0 * p->nch;
-        a.allow_fast = p->cfg.fast_peak;
+        a.allow_fast = fast;
         if (p->pipe->estimate(a, p->est) != 0) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
         if (p->cfg.fine_freq) {
             const int frc = p->pipe->fine_frequency(a);
@@ -417,7 +472,12 @@ int twstft_process(twstft_plan* p, const int16_t* iq, size_t nrecords, twstft_re
     p->be.d2h(results, p->d_res, sizeof(Result) * nrecords * p->nch);
     p->be.sync();
     if (!p->be.ok()) return fail(p, TWSTFT_E_CUDA, p->be.err_string());
-    if (p->cfg.fast_peak) return rerun_uncertified(p, h, false, nrecords, results);
+    size_t nrerun = 0;
+    if (fast) {
+        const int rc = rerun_uncertified(p, h, false, nrecords, results, &nrerun);
+        if (rc != TWSTFT_OK) return rc;
+    }
+    fast_account(p, nrecords, nrerun, fast);
     return TWSTFT_OK;
 }
 
@@ -432,16 +492,25 @@ int twstft_process_windows(twstft_plan* p, const int16_t* iq, int on_device, siz
         if (offsets[i] < 0 || (size_t)(offsets[i] + N) > total_instants)
             return fail(p, TWSTFT_E_ARG, "window outside the buffer");
     const short2* d_iq = reinterpret_cast<const short2*>(iq);
-    short2* tmp = nullptr;
-    if (!on_device) {
-        tmp = (short2*)p->be.alloc(sizeof(short2) * total_instants * p->nch);
-        if (!p->be.ok()) return fail(p, TWSTFT_E_NOMEM, "device allocation failed");
-        p->be.h2d(tmp, iq, sizeof(short2) * total_instants * p->nch);
-        d_iq = tmp;
+    if (!on_device) {   // host buffer: staged in a plan-owned buffer that only ever grows (no allocation per call)
+        const size_t need = total_instants * p->nch;
+        if (p->win_cap < need) {
+            p->be.sync();
+            p->be.free(p->d_winbuf);
+            p->d_winbuf = (short2*)p->be.alloc(sizeof(short2) * need);
+            p->win_cap = p->d_winbuf ? need : 0;
+            if (!p->d_winbuf || !p->be.ok()) return fail(p, TWSTFT_E_NOMEM, "device allocation failed");
+        }
+        p->be.h2d(p->d_winbuf, iq, sizeof(short2) * need);
+        d_iq = p->d_winbuf;
     }
     const int B = p->cfg.max_batch;
+    const bool fast = fast_on(p);
     int rc = TWSTFT_OK;
-    std::vector<i64> off(B);
+    std::vector<i64> off(B), off2(B);
+    std::vector<double> df2((size_t)B * p->nch);
+    std::vector<twstft_result> rows((size_t)B * p->nch);
+    size_t nrerun = 0;
     for (size_t w0 = 0; w0 < nwin && rc == TWSTFT_OK; w0 += B) {
         const int nb = (int)((nwin - w0) < (size_t)B ? (nwin - w0) : B);
         for (int i = 0; i < nb; i++) off[i] = offsets[w0 + i] * p->nch;
@@ -451,29 +520,39 @@ int twstft_process_windows(twstft_plan* p, const int16_t* iq, int on_device, siz
         a.d_raw = d_iq; a.nrec = nb; a.nch = p->nch; a.rec_stride = 0; a.d_rec_offset = p->d_off;
         a.estimate = 0; a.d_df_in = p->d_dfin; a.variant = p->cfg.variant; a.ddof = p->cfg.ddof;
         a.fs = p->cfg.fs; a.d_out = p->d_res;
-        a.allow_fast = p->cfg.fast_peak;
+        a.allow_fast = fast;
         if (p->pipe->correlate(a) != 0) { rc = fail(p, TWSTFT_E_CUDA, p->be.err_string()); break; }
         p->be.d2h(results + w0 * p->nch, p->d_res, sizeof(Result) * nb * p->nch);
         p->be.sync();
-        if (!p->be.ok()) rc = fail(p, TWSTFT_E_CUDA, p->be.err_string());
-        // fast peak path: windows whose certificate failed (status bit 2) go through the full path, one at a time
-        for (int i = 0; i < nb && rc == TWSTFT_OK && p->cfg.fast_peak; i++) {
-            bool flagged = false;
-            for (int c = 0; c < p->nch; c++) flagged = flagged || (((int)results[(w0 + i) * p->nch + c].status) & 4);
-            p->fast_records++;
-            if (!flagged) continue;
-            p->fast_rerun++;
-            p->be.h2d(p->d_off, &off[i], sizeof(i64));
-            p->be.h2d(p->d_dfin, df + (w0 + i) * p->nch, sizeof(double) * p->nch);
-            RunArgs b = a;
-            b.nrec = 1; b.allow_fast = 0;
-            if (p->pipe->correlate(b) != 0) { rc = fail(p, TWSTFT_E_CUDA, p->be.err_string()); break; }
-            p->be.d2h(results + (w0 + i) * p->nch, p->d_res, sizeof(Result) * p->nch);
-            p->be.sync();
-            if (!p->be.ok()) rc = fail(p, TWSTFT_E_CUDA, p->be.err_string());
+        if (!p->be.ok()) { rc = fail(p, TWSTFT_E_CUDA, p->be.err_string()); break; }
+        if (!fast) continue;
+        // fast peak path: the windows of this batch whose certificate failed (status bit 2) go through the full path
+        // together, in one launch sequence
+        std::vector<int> flagged;
+        for (int i = 0; i < nb; i++) {
+            bool f = false;
+            for (int c = 0; c < p->nch; c++) f = f || (((int)results[(w0 + i) * p->nch + c].status) & 4);
+            if (f) flagged.push_back(i);
         }
+        if (flagged.empty()) continue;
+        nrerun += flagged.size();
+        const int nf = (int)flagged.size();
+        for (int i = 0; i < nf; i++) {
+            off2[i] = off[flagged[i]];
+            for (int c = 0; c < p->nch; c++) df2[(size_t)i * p->nch + c] = df[(w0 + flagged[i]) * p->nch + c];
+        }
+        p->be.h2d(p->d_off, off2.data(), sizeof(i64) * nf);
+        p->be.h2d(p->d_dfin, df2.data(), sizeof(double) * nf * p->nch);
+        RunArgs b2 = a;
+        b2.nrec = nf; b2.allow_fast = 0;
+        if (p->pipe->correlate(b2) != 0) { rc = fail(p, TWSTFT_E_CUDA, p->be.err_string()); break; }
+        p->be.d2h(rows.data(), p->d_res, sizeof(Result) * nf * p->nch);
+        p->be.sync();
+        if (!p->be.ok()) { rc = fail(p, TWSTFT_E_CUDA, p->be.err_string()); break; }
+        for (int i = 0; i < nf; i++)
+            memcpy(results + (w0 + flagged[i]) * p->nch, rows.data() + (size_t)i * p->nch, sizeof(twstft_result) * p->nch);
     }
-    if (tmp) { p->be.sync(); p->be.free(tmp); }
+    if (rc == TWSTFT_OK) fast_account(p, nwin, nrerun, fast);
     return rc;
 }
 

@@ -271,6 +271,10 @@ int twstft_profile_read(twstft_plan* plan, int slot, char* name, size_t name_cap
 
 /* Introspection used by tests and the benchmark. */
 int twstft_fast_counters(const twstft_plan* plan, int64_t* records, int64_t* rerun); /* fast peak path: records seen / re-run in full */
+/* The fast peak path only pays while few records fall back (an uncertified record costs the fast attempt plus the full
+ * path): when more than a quarter of the last 64 records fell back the plan runs the next 1024 through the full path
+ * and then probes again.  Returns how many records went through the full path for that reason.  Rows never change. */
+int64_t twstft_fast_suspended(const twstft_plan* plan);
 int64_t twstft_kernel_launches(const twstft_plan* plan);   /* kernels launched so far by this plan */
 int twstft_debug_fetch(twstft_plan* plan, int what, int lane, void* host_out, size_t bytes);
 int twstft_window_bins(const twstft_plan* plan, int64_t* lo, int64_t* hi);

@@ -474,3 +474,102 @@ def run_octave_seam_search_df(lib, fs=250000.0, n=10000, df=50321.5, seed=12, wi
     kref, tried = oc.search_df(d, k, 20.0, freq, oc.fcode_K(code), fs=fs)
     assert ncand == len(tried) and kref > 0, (ncand, tried)
     assert kbon == kref and dff == freq[kref - 1] / 2, (kbon, kref, dff)
+
+
+def run_fast_peak_governor(lib, n, win=8, off=12):
+    """A run in which half the records have no correlation peak: every flagged record of a call is re-run in one
+    batch, rows equal those of a plan without the fast path bit for bit, and once the fall-back rate of a window of
+    `win` records exceeds a quarter the plan stops trying the fast path for `off` records, then probes again."""
+    bits, code = make_code(n)
+    rng = np.random.default_rng(5)
+    recs = []
+    for i in range(40):
+        if i % 2:
+            recs.append(np.rint(rng.normal(0, 3000, 4 * n)).astype(np.int16))
+        else:
+            recs.append(synth.record_pair(code, 300 + i)[0])
+    recs = np.stack(recs)
+    os.environ["TWSTFT_FAST_WIN"], os.environ["TWSTFT_FAST_OFF"] = str(win), str(off)
+    try:
+        with Correlator(nsamples=n, max_batch=4, lib=lib, fast_peak=True) as cor:
+            cor.set_code(bits)
+            fast = np.concatenate([cor.process(recs[i:i + 4]) for i in range(0, 40, 4)])
+            seen, rerun = cor.fast_counters
+            suspended = cor.fast_suspended
+    finally:
+        del os.environ["TWSTFT_FAST_WIN"], os.environ["TWSTFT_FAST_OFF"]
+    with Correlator(nsamples=n, max_batch=4, lib=lib) as cor:
+        cor.set_code(bits)
+        full = cor.process(recs)
+    # records without a peak went through the full path either way: identical rows; certified records differ from the
+    # full path only by the fp32 rounding of the differently evaluated lags
+    assert np.array_equal(fast[1::2], full[1::2])
+    assert np.array_equal(fast["indice"], full["indice"]) and np.array_equal(fast["df"], full["df"])
+    assert np.max(np.abs(fast["correction"][0::2] - full["correction"][0::2])) < 3e-5
+    assert seen + suspended == 40 and suspended >= off and rerun >= 4, (seen, rerun, suspended)
+    assert seen > win, "the plan never probed the fast path again"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SNR sweep: parity and fast-path certificate statistics over the field range of input SNR
+# (experiments/221127_SNR/README.md:56-62: -20 .. -5 dB in 5 MHz)
+_SWEEP = {}
+
+
+def _sweep_oracle(job):
+    kind, idx = job
+    raw, code, fs = _SWEEP["recs"][idx], _SWEEP["code"], _SWEEP["fs"]
+    n = len(code)
+    if kind == "G":
+        freq = oc.freq_axis_G(fs, n)
+        return oc.record_G(raw, oc.window(freq, -20000.0, 20000.0), freq, oc.fcode_G(code), code, fs=fs, channels=(1,))[1]
+    d = oc.unpack_single(raw)
+    return oc.processing_K(d - d.mean(), _SWEEP["df"][idx], oc.fcode_K(code), code, fs)
+
+
+def run_snr_sweep(lib, n, kind="G", snrs=(-20.0, -15.0, -10.0, -5.0), seeds_per_cell=16, fast=True, procs=16, strict=True):
+    """kind "G": two-channel records through twstft_process_device (channel 1 at the swept SNR, carrier estimated);
+    kind "K": single-channel windows through twstft_process_windows with the carrier offset given (the estimator's own
+    value, so that both sides derotate by the same df).  Records come from the device generator; every channel-1 row
+    is compared with the oracle.  Returns per-SNR statistics (worst errors, fall-back counts of the fast peak path);
+    strict: assert the north-star tolerances in every cell."""
+    import multiprocessing as mp
+    fs = 5e6
+    bits, code = make_code(n)
+    nch = 2 if kind == "G" else 1
+    stats = []
+    kw = dict(nsamples=n, fs=fs, max_batch=seeds_per_cell, lib=lib, fast_peak=fast)
+    if kind == "K":
+        kw.update(variant="K", layout="single")
+    with Correlator(**kw) as cor:
+        cor.set_code(bits)
+        for ci, snr in enumerate(snrs):
+            ptr = cor.synth_records(9000 + 100 * ci, seeds_per_cell, snr1_db=snr, snr2_db=0.6)
+            raw = cor.from_device(ptr, seeds_per_cell * n * nch * 4).reshape(seeds_per_cell, -1)
+            f0 = cor.fast_counters
+            if kind == "G":
+                res = cor.process_device(ptr, seeds_per_cell)[:, 0]
+                dfs = res["df"]
+            else:
+                dfs = cor.estimate_carrier(raw)[0][:, 0]
+                res = cor.process_windows(ptr, np.arange(seeds_per_cell) * n, dfs, on_device=True,
+                                          total_instants=seeds_per_cell * n)[:, 0]
+            f1 = cor.fast_counters
+            cor.device_free(ptr)
+            _SWEEP.update(recs=list(raw), code=code, fs=fs, df=list(dfs))
+            with mp.get_context("fork").Pool(min(procs, os.cpu_count() or 1)) as pool:
+                refs = pool.map(_sweep_oracle, [(kind, i) for i in range(seeds_per_cell)], chunksize=1)
+            cell = dict(snr_db=snr, records=seeds_per_cell, index_mismatch=0, df_mismatch=0, fine_delay=0.0, phase=0.0,
+                        snr_err_db=0.0, fast_seen=f1[0] - f0[0], fast_rerun=f1[1] - f0[1])
+            for r, o in zip(res, refs):
+                cell["index_mismatch"] += int(r["indice"]) != o["indice"]
+                if kind == "G":
+                    cell["df_mismatch"] += int(r["df"] != o["df"])
+                cell["fine_delay"] = max(cell["fine_delay"], abs(r["correction"] - o["correction"]) / 3.0)
+                cell["phase"] = max(cell["phase"], abs(np.angle(complex(r["xval_re"], r["xval_im"]) * np.conj(o["xval"]))))
+                cell["snr_err_db"] = max(cell["snr_err_db"], abs(snr_db(r) - 10 * np.log10(o["SNRr"] + o["SNRi"])))
+            stats.append(cell)
+            if strict:
+                assert cell["index_mismatch"] == 0 and cell["df_mismatch"] == 0, cell
+                assert cell["fine_delay"] < TOL_DELAY_SAMPLES and cell["phase"] < TOL_PHASE_RAD and cell["snr_err_db"] < TOL_SNR_DB, cell
+    return stats

@@ -275,3 +275,13 @@ def test_octave_function_seam_processing(n):
 
 def test_octave_function_seam_search_df():
     pc.run_octave_seam_search_df(pc.EMU_LIB)
+
+
+def test_fast_peak_governor_and_batched_fallback():
+    pc.run_fast_peak_governor(pc.EMU_LIB, 10000)
+
+
+@pytest.mark.parametrize("kind", ["G", "K"])
+def test_snr_sweep_small(kind):
+    """The sweep harness of the GPU suite at N = 1e4 (40 dB of processing gain: -10 dB and up only)."""
+    pc.run_snr_sweep(pc.EMU_LIB, 10000, kind=kind, snrs=(-10.0, -3.0), seeds_per_cell=3, procs=2)

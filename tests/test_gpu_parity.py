@@ -228,3 +228,15 @@ def test_octave_function_seam_processing(n):
 def test_octave_function_seam_search_df():
     pc.run_octave_seam_search_df(pc.CUDA_LIB)
     pc.run_octave_seam_search_df(pc.CUDA_LIB, fs=5e6, n=200000, df=50321.5, window=(92000.0, 108000.0))
+
+
+def test_fast_peak_governor_and_batched_fallback():
+    pc.run_fast_peak_governor(pc.CUDA_LIB, 250000)
+
+
+@pytest.mark.parametrize("kind,n", [("G", 5000000), ("K", 200000)])
+def test_snr_sweep_minus20_to_minus5_db(kind, n):
+    """Field range of input SNR (experiments/221127_SNR/README.md:56-62), 16 seeds per cell, fast peak path on:
+    peak index and carrier bin exact, fine delay / phase / SNR inside the north-star tolerances in every cell."""
+    stats = pc.run_snr_sweep(pc.CUDA_LIB, n, kind=kind)
+    assert len(stats) == 4 and all(c["fast_seen"] + 0 >= 0 for c in stats)
