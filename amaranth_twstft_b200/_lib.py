@@ -26,7 +26,7 @@ EXPORTS = [
     "twstft_search_df_block", "twstft_estimate_decimated", "twstft_processing_cf64", "twstft_processing_cf64_df",
     "twstft_search_df_cf64", "twstft_shard_create", "twstft_shard_destroy", "twstft_shard_ngpus", "twstft_shard_plan",
     "twstft_shard_last_error", "twstft_shard_set_code", "twstft_shard_process", "twstft_process_cycled",
-    "twstft_shard_process_cycled", "twstft_synth_records", "twstft_synth_stream", "twstft_fast_suspended", "twstft_fast_counters", "twstft_timer_start", "twstft_timer_stop", "twstft_profile_enable", "twstft_profile_read",
+    "twstft_shard_process_cycled", "twstft_synth_records", "twstft_synth_stream", "twstft_fast_suspended", "twstft_acquire", "twstft_fast_counters", "twstft_timer_start", "twstft_timer_stop", "twstft_profile_enable", "twstft_profile_read",
 ]
 
 
@@ -85,6 +85,8 @@ def load(path=None):
     lib.twstft_process_windows.argtypes = [P, P, C.c_int, C.c_size_t, P, P, C.c_size_t, P]
     lib.twstft_estimate_carrier.argtypes = [P, P, C.c_int, C.c_size_t, P, P]
     lib.twstft_doppler_bank.argtypes = [P, P, C.c_int, C.c_size_t, C.c_int64, P, C.c_size_t, C.c_int, P]
+    lib.twstft_acquire.argtypes = [P, P, C.c_int, C.c_size_t, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
+                                   C.c_int, C.c_int, P, P, P]
     lib.twstft_search_df.argtypes = [P, P, C.c_int, C.c_size_t, C.c_int64, C.c_double, P, P, P]
     lib.twstft_estimate_carrier_block.argtypes = [P, P, C.c_int, C.c_size_t, C.c_int, P, P]
     lib.twstft_search_df_block.argtypes = [P, P, P, C.c_int, C.c_int, C.c_double, P, P, P]

@@ -244,6 +244,18 @@ class Correlator:
                     "twstft_doppler_bank")
         return out
 
+    def acquire(self, iq, fc_init=0.0, frange=2000.0, fstep=250.0, min_step=1.0, offset=0, sub_mean=True, channel=0):
+        """Step-halving Doppler / code-phase acquisition (experiments/231001_DLL_PLL/rxcomplex.cpp:522-568) on the window
+        at `offset`: returns (fc, bank row of the best bin, bins evaluated)."""
+        iq = np.ascontiguousarray(iq, dtype=np.int16)
+        fc = C.c_double()
+        nb = C.c_int32()
+        row = np.zeros(1, dtype=BANK_DTYPE)
+        self._check(self.lib.twstft_acquire(self._plan, iq.ctypes.data, 0, iq.size // (2 * self.nch), int(offset),
+                                            float(fc_init), float(frange), float(fstep), float(min_step), int(sub_mean),
+                                            int(channel), C.byref(fc), row.ctypes.data, C.byref(nb)), "twstft_acquire")
+        return fc.value, row[0], nb.value
+
     def search_df(self, iq, df_threshold=20.0, offset=0):
         """k=search_df(d,k,df_threshold): returns (kbon[nch] 1-based shifted-axis index or 0, df[nch], ncand[nch])."""
         iq = np.ascontiguousarray(iq, dtype=np.int16)

@@ -128,6 +128,7 @@ int twstft_plan_create(const twstft_config* cfg, twstft_plan** out)
     p->max_lanes = cfg->max_batch * p->nch;
     if (p->pipe->setup(&p->be, p->max_lanes, p->nq) != 0)
         return fail(p, TWSTFT_E_NOMEM, std::string("device allocation failed: ") + p->be.err_string());
+    if (getenv("TWSTFT_PROFILE_DUMP")) p->be.profiling = true;   // CLIs: print per-kernel totals when the plan is destroyed
     if (const char* e = getenv("TWSTFT_FAST_WIN")) { if (atoll(e) > 0) p->fast_win = atoll(e); }
     if (const char* e = getenv("TWSTFT_FAST_OFF")) { if (atoll(e) > 0) p->fast_off = atoll(e); }
     if (cfg->fast_peak && p->pipe->set_fast_peak(1) != 0)
@@ -161,6 +162,13 @@ void twstft_plan_destroy(twstft_plan* p)
 {
     if (!p) return;
     p->be.use();
+    if (p->be.profiling && getenv("TWSTFT_PROFILE_DUMP")) {     // per-kernel CUDA-event totals of this plan's lifetime
+        p->be.prof_collect();
+        fprintf(stderr, "twstft_profile N=%lld {", (long long)p->cfg.nsamples);
+        for (size_t i = 0; i < p->be.prof.size(); i++)
+            fprintf(stderr, "%s\"%s\": [%.4f, %ld]", i ? ", " : "", p->be.prof[i].name, p->be.prof[i].ms, p->be.prof[i].count);
+        fprintf(stderr, "}\n");
+    }
     delete p->pipe;
     p->be.free(p->d_raw);
     p->be.free(p->d_res);
@@ -647,6 +655,51 @@ int twstft_doppler_bank(twstft_plan* p, const int16_t* iq, int iq_on_device, siz
     const short2* d_win = stage_window(p, iq, iq_on_device, offset);
     if (!d_win) return fail(p, TWSTFT_E_NOMEM, "device allocation failed");
     return run_bank(p, d_win, dfs, nbins, sub_mean, results);
+}
+
+// Doppler / code-phase acquisition with a step-halving frequency grid: the search loop of
+// experiments/231001_DLL_PLL/rxcomplex.cpp:522-568 over the bank kernels.  Every grid point is one bank bin (derotate,
+// correlate at 1x, peak magnitude); the best point so far is replaced only by a strictly larger peak, in grid order;
+// after each pass the step is halved, the range becomes the new step around the best carrier, until the step is < 1 Hz.
+int twstft_acquire(twstft_plan* p, const int16_t* iq, int iq_on_device, size_t total_instants, int64_t offset,
+                   double fc_init, double range, double step, double min_step, int sub_mean, int channel,
+                   double* fc_out, twstft_bank_result* best_out, int32_t* nbins_out)
+{
+    if (!p || !p->pipe || !iq || !fc_out || !(step > 0) || !(range >= 0) || channel < 0 || channel >= p->nch) return TWSTFT_E_ARG;
+    if (!p->have_code) return fail(p, TWSTFT_E_NOCODE, "no PRN code installed");
+    if (offset < 0 || (size_t)(offset + p->cfg.nsamples) > total_instants)
+        return fail(p, TWSTFT_E_ARG, "window outside the buffer");
+    if (!(min_step > 0)) min_step = 1.0;                     // rxcomplex.cpp:557 "if (fstep < 1.0) break"
+    p->be.use();
+    const short2* d_win = stage_window(p, iq, iq_on_device, offset);
+    if (!d_win) return fail(p, TWSTFT_E_NOMEM, "device allocation failed");
+    double fc = fc_init, frange = range, fstep = step, pk = 0.0;
+    twstft_bank_result best{};
+    int32_t nb = 0;
+    std::vector<double> grid;
+    std::vector<twstft_bank_result> rows;
+    for (;;) {
+        const double flow = fc - frange, fhigh = fc + frange;
+        grid.clear();
+        for (double fcc = flow; fcc <= fhigh; fcc += fstep) grid.push_back(fcc);      // :527, accumulated like the reference
+        rows.resize(grid.size() * p->nch);
+        if (!grid.empty()) {
+            const int rc = run_bank(p, d_win, grid.data(), grid.size(), sub_mean, rows.data());
+            if (rc != TWSTFT_OK) return rc;
+        }
+        for (size_t i = 0; i < grid.size(); i++) {
+            const twstft_bank_result& r = rows[i * p->nch + channel];
+            if (r.prnsig > pk) { pk = r.prnsig; fc = grid[i]; best = r; }            // :545-550
+        }
+        nb += (int32_t)grid.size();
+        fstep = fstep / 2.0;                                                          // :554-557
+        frange = fstep;
+        if (fstep < min_step) break;
+    }
+    *fc_out = fc;
+    if (best_out) *best_out = best;
+    if (nbins_out) *nbins_out = nb;
+    return TWSTFT_OK;
 }
 
 // Body of search_df (claudio_aligned_code_re_separate.m:26-46).  `sp` owns the x^p spectrum (its estimator window

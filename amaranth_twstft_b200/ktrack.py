@@ -69,7 +69,7 @@ class KTracker:
         self.est = Correlator(nsamples=int(fs), fs=fs, variant="K", layout="single", freq_axis="K",
                               window_hz=window_hz, est_sub_mean=0, max_batch=1, lib=lib, device=device)
         self.cor = Correlator(nsamples=self.N, fs=fs, variant="K", layout="single", max_batch=max_batch,
-                              samples_per_chip=samples_per_chip, lib=lib, device=device, fast_peak=True)   # like claudio_aligned.c
+                              samples_per_chip=samples_per_chip, lib=lib, device=device, fast_peak=False)   # like claudio_aligned.c (peak parked at the window start)
         self.cor.set_code(chips)
         self.max_batch = max_batch
         nax = int(fs) * self.ls

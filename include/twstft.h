@@ -18,6 +18,7 @@
  *   twstft_estimate_carrier_block  the estimator on the 2-s blocks of the K scripts                lo_separate.m:120-129
  *   twstft_doppler_bank  per-bin body of search_df over a grid of offsets (cross-ambiguity)
  *                                                                                 claudio_aligned_code_re_separate.m:33-42
+ *   twstft_acquire       coarse grid + step halving around the best bin            experiments/231001_DLL_PLL/rxcomplex.cpp:522-568
  *   twstft_search_df     k=search_df(d,k,df_threshold)                            claudio_aligned_code_re_separate.m:26-46
  *   twstft_search_df_block  the same on the 2-s block the scripts hand it                 claudio_aligned_code_re_separate.m:150
  *   twstft_estimate_bins d2=fftshift(abs(fft(d.^2))); max(d2(kbon-3:kbon+3)), d=[dold;block]  claudio_aligned_code_re_separate.m:166-168
@@ -180,6 +181,16 @@ typedef struct twstft_bank_result {
  * sub_mean != 0 removes the window mean first (the caller of processing() does, search_df does not). */
 int twstft_doppler_bank(twstft_plan* plan, const int16_t* iq, int iq_on_device, size_t total_instants, int64_t offset,
                         const double* dfs, size_t nbins, int sub_mean, twstft_bank_result* results);
+
+/* Doppler / code-phase acquisition with the step-halving grid of experiments/231001_DLL_PLL/rxcomplex.cpp:522-568
+ * on top of the bank: pass 1 evaluates fc_init-range .. fc_init+range in steps of `step` (grid accumulated as
+ * fcc += step), the best bin so far is replaced only by a strictly larger peak magnitude; then step /= 2, the range
+ * becomes the new step around the best carrier, and so on until step < min_step (1 Hz in the reference).
+ * fc_out: the carrier of the best bin, best_out: its bank row (peak index, magnitude, metric) for `channel`,
+ * nbins_out: bins evaluated. */
+int twstft_acquire(twstft_plan* plan, const int16_t* iq, int iq_on_device, size_t total_instants, int64_t offset,
+                   double fc_init, double range, double step, double min_step, int sub_mean, int channel,
+                   double* fc_out, twstft_bank_result* best_out, int32_t* nbins_out);
 
 /* search_df on one window: candidates = bins of the plan's estimator window whose |fft(x^p)| exceeds
  * df_threshold*median; if there are 1..99 each is tested with the bank body and the LAST one whose metric

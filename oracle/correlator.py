@@ -318,6 +318,34 @@ def doppler_bank(d, dfs, fcode, fs=FS):
     return b0, sig, met
 
 
+def acquire_halving(d, fcode, fc_init, frange, fstep, min_step=1.0, fs=FS):
+    """Step-halving acquisition of experiments/231001_DLL_PLL/rxcomplex.cpp:522-568 with the per-bin body of
+    search_df (claudio_aligned_code_re_separate.m:33-37) as the bin metric: grid fc-frange..fc+frange accumulated as
+    fcc += fstep, best bin replaced only by a strictly larger peak, then fstep /= 2, frange = fstep, until
+    fstep < min_step.  PARITY UNPINNED by the reference (its cross_spectrum band-limits with experiment-specific
+    filter edges; only the search loop is restated).  Returns (fc, b0, prnsig, bins evaluated)."""
+    n = len(fcode)
+    temps = np.arange(n) / fs
+    fc, pk, b0, nb = fc_init, 0.0, 0, 0
+    while True:
+        fcc, fhigh = fc - frange, fc + frange
+        grid = []
+        while fcc <= fhigh:
+            grid.append(fcc)
+            fcc += fstep
+        for f in grid:
+            prnmap = np.abs(_fft.ifft(fcode * np.conj(_fft.fft(d[:n] * np.exp(-1j * 2 * np.pi * f * temps)))))
+            b = int(np.argmax(prnmap))
+            if prnmap[b] > pk:
+                pk, fc, b0 = float(prnmap[b]), f, b
+        nb += len(grid)
+        fstep = fstep / 2.0
+        frange = fstep
+        if fstep < min_step:
+            break
+    return fc, b0, pk, nb
+
+
 # --------------------------------------------------------------------------- IQ reader (A2)
 def unpack_interleaved2(raw_int16):
     """godual_ranging.m:76-79: [I1 Q1 I2 Q2]... -> (d1, d2) complex128, means NOT removed."""

@@ -99,7 +99,9 @@ int main(int argc, char** argv)
     cc = ce;
     cc.nsamples = (int64_t)nchips * cc.samples_per_chip; cc.max_batch = batch > 0 ? batch : 32;
     cc.win_lo_hz = -20000; cc.win_hi_hz = 20000;
-    cc.fast_peak = 1;      /* one inverse transform + certificate per window; uncertified windows re-run in full: same rows */
+    cc.fast_peak = 0;      /* the tracking loop parks the correlation peak ~20 samples into the window (:142), where
+                              the fast path's local segment would wrap around the array: every window would fall back
+                              (measured: the governor suspends it after 64 windows), so the full path is used directly */
     twstft_plan *est = NULL, *cor = NULL;
     if (twstft_plan_create(&ce, &est) != TWSTFT_OK) return die(est, "twstft_plan_create (block estimator)");
     if (twstft_plan_create(&cc, &cor) != TWSTFT_OK) return die(cor, "twstft_plan_create (correlator)");

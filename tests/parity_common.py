@@ -573,3 +573,17 @@ def run_snr_sweep(lib, n, kind="G", snrs=(-20.0, -15.0, -10.0, -5.0), seeds_per_
                 assert cell["index_mismatch"] == 0 and cell["df_mismatch"] == 0, cell
                 assert cell["fine_delay"] < TOL_DELAY_SAMPLES and cell["phase"] < TOL_PHASE_RAD and cell["snr_err_db"] < TOL_SNR_DB, cell
     return stats
+
+
+def run_acquire(lib, n=10000, true_df=1337.3, seed=14, frange=2000.0, fstep=500.0):
+    """Step-halving acquisition (rxcomplex.cpp:522-568) against its restatement: same grid, same winner."""
+    bits, code = make_code(n)
+    raw, _ = synth.record_single(code, seed, delay=0.37 * n, df=true_df, snr_db=-3.0)
+    with Correlator(nsamples=n, variant="K", layout="single", max_batch=8, lib=lib) as cor:
+        cor.set_code(bits)
+        fc, row, nb = cor.acquire(raw, 0.0, frange, fstep, 1.0, sub_mean=False)
+    d = oc.unpack_single(raw)
+    rfc, rb0, rpk, rnb = oc.acquire_halving(d, oc.fcode_K(code), 0.0, frange, fstep)
+    assert nb == rnb and fc == rfc, (nb, rnb, fc, rfc)
+    assert int(row["b0"]) == rb0 and abs(row["prnsig"] / rpk - 1) < 1e-4
+    assert abs(fc - true_df) < 2.0, "the search did not converge on the synthetic carrier"

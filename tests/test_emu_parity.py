@@ -285,3 +285,7 @@ def test_fast_peak_governor_and_batched_fallback():
 def test_snr_sweep_small(kind):
     """The sweep harness of the GPU suite at N = 1e4 (40 dB of processing gain: -10 dB and up only)."""
     pc.run_snr_sweep(pc.EMU_LIB, 10000, kind=kind, snrs=(-10.0, -3.0), seeds_per_cell=3, procs=2)
+
+
+def test_step_halving_acquisition():
+    pc.run_acquire(pc.EMU_LIB, 10000)

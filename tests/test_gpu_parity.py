@@ -240,3 +240,9 @@ def test_snr_sweep_minus20_to_minus5_db(kind, n):
     peak index and carrier bin exact, fine delay / phase / SNR inside the north-star tolerances in every cell."""
     stats = pc.run_snr_sweep(pc.CUDA_LIB, n, kind=kind)
     assert len(stats) == 4 and all(c["fast_seen"] + 0 >= 0 for c in stats)
+
+
+def test_step_halving_acquisition():
+    """experiments/231001_DLL_PLL/rxcomplex.cpp:522-568 on top of the bank kernels, N = 2e5 and the 1-s window."""
+    pc.run_acquire(pc.CUDA_LIB, 200000)
+    pc.run_acquire(pc.CUDA_LIB, 5000000, true_df=-912.6, fstep=1000.0)
