@@ -21,7 +21,7 @@ TOL_SNR_DB = 0.01
 CODES = {  # window length -> (bitlen, taps, noiselen): all from experiments/221207_twoway_codes/codes
     10000: (13, 27, 5000),
     20000: (14, 43, 10000),
-    50000: (17, 3, 25000),
+    50000: (15, 3, 25000),          # the file is named ..._bitlen17_taps03 but holds a 15-bit sequence (tests/golden/prn_digests.json)
     500000: (18, 39, 250000),
     200000: (17, 9, 100000),
     250000: (17, 9, 125000),
@@ -587,3 +587,44 @@ def run_acquire(lib, n=10000, true_df=1337.3, seed=14, frange=2000.0, fstep=500.
     assert nb == rnb and fc == rfc, (nb, rnb, fc, rfc)
     assert int(row["b0"]) == rb0 and abs(row["prnsig"] / rpk - 1) < 1e-4
     assert abs(fc - true_df) < 2.0, "the search did not converge on the synthetic carrier"
+
+
+def run_edge_peak(lib, n=10000):
+    """godual_ranging.m:31-32 would index out of range when the peak is the first/last sample; the library wraps
+    and raises bit0 of status instead; the rows are the oracle's (which wraps too)."""
+    bits, code = make_code(n)
+    raw, _ = synth.record_pair(code, 5, ch1=dict(delay=0.0, snr_db=10.0), ch2=dict(delay=n - 1.0 / 3.0, snr_db=10.0))
+    for fast in (False, True):
+        with Correlator(nsamples=n, max_batch=1, lib=lib, fast_peak=fast) as cor:
+            cor.set_code(bits)
+            res = cor.process(raw)
+        assert int(res[0, 0]["indice"]) == 1 and int(res[0, 0]["status"]) & 1
+        assert int(res[0, 1]["indice"]) == 3 * n and int(res[0, 1]["status"]) & 1
+        freq = oc.freq_axis_G(5e6, n)
+        ref = oc.record_G(raw, oc.window(freq, -20000, 20000), freq, oc.fcode_G(code), code)
+        assert_row_matches(res[0, 0], ref[1], where="edge ch1")
+        assert_row_matches(res[0, 1], ref[2], where="edge ch2")
+
+
+def run_no_peak_vs_oracle(lib, n, seed=31):
+    """Records WITHOUT a correlation peak (noise only; a tone next to noise) against the ORACLE, with and without the
+    fast peak path: the arg-max then sits among noise samples, where fp32 and fp64 must still agree on the index."""
+    bits, code = make_code(n)
+    rng = np.random.default_rng(seed)
+    noise = np.rint(rng.normal(0, 3000, 4 * n)).astype(np.int16)
+    t = np.arange(n)
+    tone = np.rint(2000 * np.exp(2j * np.pi * 0.01234 * t))
+    tone_rec = np.rint(rng.normal(0, 300, 4 * n)).astype(np.int16)
+    tone_rec[0::4] += tone.real.astype(np.int16)
+    tone_rec[1::4] += tone.imag.astype(np.int16)
+    recs = np.stack([noise, tone_rec])
+    freq = oc.freq_axis_G(5e6, n)
+    k = oc.window(freq, -20000, 20000)
+    refs = [oc.record_G(r, k, freq, oc.fcode_G(code), code) for r in recs]
+    for fast in (False, True):
+        with Correlator(nsamples=n, max_batch=2, lib=lib, fast_peak=fast) as cor:
+            cor.set_code(bits)
+            res = cor.process(recs)
+        for i in range(2):
+            for ch in (1, 2):
+                assert_row_matches(res[i, ch - 1], refs[i][ch], where=f"no-peak record {i} ch{ch} fast={fast}")

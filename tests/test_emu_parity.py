@@ -164,20 +164,11 @@ def test_variant_k_window_offsets_in_long_buffer():
 
 
 def test_variant_g_peak_at_array_edge_sets_status():
-    """godual_ranging.m:31-32 would index out of range when the peak is the first/last sample; the
-    library wraps and raises bit0 of status instead."""
-    n = 10000
-    bits, code = pc.make_code(n)
-    raw, _ = synth.record_pair(code, 5, ch1=dict(delay=0.0, snr_db=10.0), ch2=dict(delay=n - 1.0 / 3.0, snr_db=10.0))
-    with Correlator(nsamples=n, max_batch=1, lib=pc.EMU_LIB) as cor:
-        cor.set_code(bits)
-        res = cor.process(raw)
-    assert int(res[0, 0]["indice"]) == 1 and int(res[0, 0]["status"]) & 1
-    assert int(res[0, 1]["indice"]) == 3 * n and int(res[0, 1]["status"]) & 1
-    freq = oc.freq_axis_G(5e6, n)
-    ref = oc.record_G(raw, oc.window(freq, -20000, 20000), freq, oc.fcode_G(code), code)
-    pc.assert_row_matches(res[0, 0], ref[1], where="edge ch1")
-    pc.assert_row_matches(res[0, 1], ref[2], where="edge ch2")
+    pc.run_edge_peak(pc.EMU_LIB, 10000)
+
+
+def test_records_without_a_peak_match_the_oracle():
+    pc.run_no_peak_vs_oracle(pc.EMU_LIB, 10000)
 
 
 def test_estimate_carrier_only():

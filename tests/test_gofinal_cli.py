@@ -1,6 +1,7 @@
 """processing/C/gofinal.c (host-only): the text reducers processing/Octave/gofinal_{op,ltfb}.m and tw.m in C, checked
 against their numpy restatement (oracle/reduce.py) on synthetic result files in the Octave and the C++ flavours."""
 import gzip
+import json
 import os
 import subprocess
 import time
@@ -140,3 +141,45 @@ def test_two_way_combination(exe, tmp_path):
     assert abs(float(out.split("std=")[1].split()[0]) - std) < 1e-5
     assert abs(float(out.split("mean=")[1].split()[0]) - mean) < 1e-5
     assert int(out.split("\nn=")[1]) == n
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Pinned by the reference's OWN reducer outputs (tests/golden/ref_op.txt, ref_ltfb.txt: one of the 413 file pairs under
+# experiments/230111_twstft_2M5/{OP,LTFB}; tools/make_golden.py also checked the row grammar of all 78 413 rows)
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _parse(path):
+    import calendar
+    text = open(path, "rb").read().decode()
+    head, body = text.split("\r\n", 1)
+    rows = []
+    for ln in body.split("\n"):
+        if ln:
+            f = ln.split("\t")
+            rows.append((calendar.timegm(time.strptime(f[0], "%Y %m %d %H %M %S")),) + tuple(float(v) for v in f[1:]))
+    return head, body.split("\n"), rows
+
+
+@pytest.mark.parametrize("name", ["ref_op.txt", "ref_ltfb.txt"])
+def test_row_format_reproduces_the_reference_files_byte_for_byte(name):
+    """The rows gofinal writes are compared with _fmt() above; _fmt() of the values parsed from the reference's own
+    files gives those files back, so the format (header, \\r\\n after the header only, %.12f/%.3f/%.1f) is the reference's."""
+    head, lines, rows = _parse(os.path.join(GOLD, name))
+    assert head == "% y  m  d  h  m  s\tdelay\t\tdf1\tSNR1\tdf2\tSNR2\tdelayrem\t\tdf1rem\tSNR1rem"
+    assert _fmt(rows) == [ln for ln in lines if ln]
+    census = json.load(open(os.path.join(GOLD, "ref_txt_census.json")))
+    assert census["files"] >= 400 and census["rows_not_matching_the_grammar"] == 0
+
+
+def test_two_way_combination_of_the_reference_files(exe, tmp_path):
+    """tw.m on a file pair the reference shipped: gofinal tw parses them as they are and agrees with the restatement."""
+    out = subprocess.run([exe, "tw", os.path.join(GOLD, "ref_op.txt"), os.path.join(GOLD, "ref_ltfb.txt")],
+                         capture_output=True, text=True, check=True).stdout
+    op_r, lt_r = (np.loadtxt(os.path.join(GOLD, n), comments="%") for n in ("ref_op.txt", "ref_ltfb.txt"))
+    ref = orr.two_way(op_r, lt_r)
+    assert f"diff={ref[0]}" in out
+    if len(ref) > 1:
+        assert abs(float(out.split("std=")[1].split()[0]) - ref[1]) < 1e-5
+        assert abs(float(out.split("mean=")[1].split()[0]) - ref[2]) < 1e-5
+        assert int(out.split("\nn=")[1]) == ref[3]

@@ -246,3 +246,12 @@ def test_step_halving_acquisition():
     """experiments/231001_DLL_PLL/rxcomplex.cpp:522-568 on top of the bank kernels, N = 2e5 and the 1-s window."""
     pc.run_acquire(pc.CUDA_LIB, 200000)
     pc.run_acquire(pc.CUDA_LIB, 5000000, true_df=-912.6, fstep=1000.0)
+
+
+def test_variant_g_peak_at_array_edge_sets_status():
+    pc.run_edge_peak(pc.CUDA_LIB, 250000)
+
+
+@pytest.mark.parametrize("n", [250000, 5000000])
+def test_records_without_a_peak_match_the_oracle(n):
+    pc.run_no_peak_vs_oracle(pc.CUDA_LIB, n)

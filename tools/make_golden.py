@@ -11,6 +11,8 @@ Reads /root/reference (read-only) and writes small fixtures:
                      last line is dropped and, for the small cases, the module constant fs is set)
                      on seeded synthetic records from amaranth_twstft_b200.synth.
   mat_schema.json    variable names / shapes / dtypes of reference result .mat files.
+  ref_op.txt, ref_ltfb.txt, ref_txt_census.json   one pair of the reference's own *op.txt / *ltfb.txt reducer outputs
+                     (experiments/230111_twstft_2M5) and a census of the row grammar over all 414 shipped files
 The GPU box has no /root/reference: tests only read the fixtures.
 """
 import glob
@@ -157,9 +159,31 @@ def make_mat_schema():
     json.dump(out, open(os.path.join(OUT, "mat_schema.json"), "w"), indent=1)
 
 
+def make_text_fixtures():
+    """One pair of the reference's OWN reducer outputs (gofinal_op.m / gofinal_ltfb.m rows, 414 such files ship under
+    experiments/230111_twstft_2M5/{OP,LTFB}): pins the row format and feeds the `tw` combination."""
+    for src, dst in (("experiments/230111_twstft_2M5/OP/1673442361.1673442552.59955op.txt.gz", "ref_op.txt"),
+                     ("experiments/230111_twstft_2M5/LTFB/1673442372ltfb.txt.gz", "ref_ltfb.txt")):
+        open(os.path.join(OUT, dst), "wb").write(read_maybe_gz(os.path.join(REF, src)))
+    # every shipped file has the same header and row grammar: record that as a count
+    rowre = re.compile(rb"^\d{4} \d\d \d\d \d\d \d\d \d\d(\t-?\d+\.\d{12}\t-?\d+\.\d{3}\t-?(\d+\.\d|Inf|NaN)){3}$")
+    n_files = n_rows = bad = 0
+    for path in sorted(glob.glob(os.path.join(REF, "experiments/230111_twstft_2M5/*/*[pb].txt.gz"))):
+        lines = read_maybe_gz(path).split(b"\n")
+        n_files += 1
+        assert lines[0].rstrip(b"\r") == b"% y  m  d  h  m  s\tdelay\t\tdf1\tSNR1\tdf2\tSNR2\tdelayrem\t\tdf1rem\tSNR1rem", path
+        for ln in lines[1:]:
+            if ln:
+                n_rows += 1
+                bad += rowre.match(ln) is None
+    json.dump({"files": n_files, "rows": n_rows, "rows_not_matching_the_grammar": bad},
+              open(os.path.join(OUT, "ref_txt_census.json"), "w"), indent=1)
+    print("text fixtures:", n_files, "files,", n_rows, "rows,", bad, "outside the row grammar")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    what = sys.argv[1:] or ["prn", "parabola", "mat", "refpy"]
+    what = sys.argv[1:] or ["prn", "parabola", "mat", "refpy", "text"]
     if "prn" in what:
         make_prn()
     if "parabola" in what:
@@ -168,3 +192,5 @@ if __name__ == "__main__":
         make_mat_schema()
     if "refpy" in what:
         make_ref_py()
+    if "text" in what:
+        make_text_fixtures()
