@@ -206,6 +206,43 @@ template <class S, class Acc> HD void dif_stage_mid(int j, float2* v, const floa
     }
 }
 
+// ---- middle stage, OUTPUT-PRUNED (radix 20 = 4 x 5 prime-factor form): only the outputs k1 whose bit is set in
+// `mask` are formed, twiddled and stored.  The estimator row passes need the few bins of a row that fall inside the
+// carrier window, i.e. a handful of (k0 + 20 k1) groups: the five radix-4 butterflies of the first PFA half are
+// shared, each wanted output then costs one five-term dot product with constant roots instead of its share of four
+// radix-5 butterflies, 19 twiddles and 20 stores.  The mask is uniform over the CTA (no divergence).
+template <class S, class Acc> HD void dif_stage_mid_pruned(int j, float2* v, const float2* tw, const Acc& acc, unsigned mask)
+{
+    static_assert(S::R1 == 20 && S::SD1::B == S::R1, "pruned middle stage: radix 20, every twiddle power tabulated");
+    static_assert((S::L / S::R1) / S::NTS == 1, "one middle-stage butterfly per thread");
+    int k0, i2;
+    mid_map<S>(j, k0, i2);
+    float2* p = acc.at(k0, i2);
+    float2 t[4][5];
+#pragma unroll
+    for (int n2 = 0; n2 < 5; n2++) {
+        float2 c[4];
+#pragma unroll
+        for (int n1 = 0; n1 < 4; n1++) c[n1] = p[((5 * n1 + 4 * n2) % 20) * S::R2 * Acc::unit()];
+        Bfly<4>::run(c);
+#pragma unroll
+        for (int ka = 0; ka < 4; ka++) t[ka][n2] = c[ka];
+    }
+    const float2* tb = tw + S::OFF_B1 + i2;
+#pragma unroll
+    for (int k1 = 0; k1 < 20; k1++) {
+        if (mask & (1u << k1)) {
+            const int ka = k1 % 4, kb = k1 % 5;       // output k of the 4 x 5 map: (k mod 4, k mod 5)
+            float2 y = t[ka][0];
+#pragma unroll
+            for (int n2 = 1; n2 < 5; n2++) y = cadd(y, mul_root<20>(t[ka][n2], 4 * n2 * kb));      // W_5^(n2 kb) = W_20^(4 n2 kb)
+            if (k1 > 0) y = cmul(y, tb[(k1 - 1) * S::R2]);
+            p[k1 * S::R2 * Acc::unit()] = y;
+        }
+    }
+    (void)v;
+}
+
 // ---- last stage (NSTAGE >= 2): digit i_last (stride 1); results stay in registers ---------------
 template <class S, class Acc> HD void dif_stage_last(int j, float2* v, const Acc& acc)
 {

@@ -40,6 +40,8 @@ struct RowParams {
     int bmul;
     i64 badd, nbig;
     int oa1, ob1, oa2, ob2;  // k2 ranges that can intersect the window (superset; exact test follows)
+    unsigned k1mask;         // != 0: output-pruned form (KRow::PRUNABLE): bit k1 set <=> some k2 = k0 + R0 k1 + R0 R1 m of
+                             // those ranges needs the middle-stage output k1; the last stage is then one dot product per bin
     // ROW_FWD_WINMAG
     float* winmag;           // [lane][win_hi - win_lo + 1]  |X|^2 at shifted index s = win_lo + i
 };
@@ -56,7 +58,10 @@ template <class S, int RPC, int MODE> struct KRow {
     static constexpr int MINB = (S::L * RPC >= 8000) ? 2 : 4;
     typedef RowAcc<S::SP0> Acc;
     static constexpr int ROWSM = (S::R0 * Acc::BSTRIDE + 1) & ~1;      // padded row (float2 units)
-    static constexpr int NG = 0;
+    // estimator modes on the 20.20.20 rows: middle and last stage output-pruned when the window is narrow (k1mask)
+    static constexpr bool PRUNABLE = (MODE != ROW_FWD_STORE) && S::NSTAGE == 3 && S::R0 == 20 && S::R1 == 20 && S::R2 == 20 &&
+                                     RPC == 1;
+    static constexpr int NG = PRUNABLE ? S::RLAST : 0;          // W_20^i, i = 0..19 (last-stage dot products)
     static constexpr int OFF_G = S::BLOB_PAD;
     static constexpr int OFF_DATA = OFF_G + ((NG + 1) & ~1);
     static constexpr int NCOMP = S::NSTAGE == 1 ? 2 : S::NSTAGE;       // 1-stage: phase 0 = tables only
@@ -124,6 +129,44 @@ template <class S, int RPC, int MODE> struct KRow {
         }
     }
 
+    // one spectrum bin of row `row`, output index o: exact window test on the fftshift'ed axis, then key / magnitude
+    static HD void emit_bin(const Params& p, i64 lane, int row, int o, float2 x, u64& best)
+    {
+        const i64 half = p.nbig / 2;
+        i64 s = ((i64)row + (i64)p.N1 * o) * p.bmul + p.badd + half;
+        if (s >= p.nbig) s -= p.nbig;
+        if (s >= p.win_lo && s <= p.win_hi) {
+            if (MODE == ROW_FWD_ARGMAX) {
+                const u64 k = make_key(cnorm(x), (unsigned)s);
+                best = k > best ? k : best;
+            } else if (MODE == ROW_FWD_WINMAG) {
+                p.winmag[lane * (p.win_hi - p.win_lo + 1) + (s - p.win_lo)] = cnorm(x);
+            }
+        }
+    }
+
+    // output-pruned last stage: thread t of the row forms the t-th wanted bin as a 20-term dot product over i2
+    static HD void pruned_last(const Params& p, const Work& wk, int j, Regs& r, const Acc& acc, const float2* w20)
+    {
+        const int n1 = p.ob1 >= p.oa1 ? p.ob1 - p.oa1 + 1 : 0, n2 = p.ob2 >= p.oa2 ? p.ob2 - p.oa2 + 1 : 0;
+        u64 best = 0;
+        for (int t = j; t < n1 + n2; t += S::NTS) {
+            const int o = t < n1 ? p.oa1 + t : p.oa2 + (t - n1);
+            const int jb = o % S::NSLAST, m = o / S::NSLAST;
+            const float2* q = acc.at(jb % S::R0, (jb / S::R0) * S::RLAST);
+            float2 x = q[0];
+            int e = 0;
+#pragma unroll
+            for (int i2 = 1; i2 < S::RLAST; i2++) {
+                e += m;
+                if (e >= S::RLAST) e -= S::RLAST;
+                x = cadd(x, cmul(q[i2 * Acc::unit()], w20[e]));
+            }
+            emit_bin(p, wk.lane, wk.rowblk * RPC, o, x, best);
+        }
+        if (MODE == ROW_FWD_ARGMAX) r.key = best;
+    }
+
     static HD void epilogue(const Params& p, const Work& wk, int rl, int j, Regs& r, const float2* g)
     {
         const int row = wk.rowblk * RPC + rl;
@@ -179,6 +222,7 @@ template <class S, int RPC, int MODE> struct KRow {
     {
         float2* sm = reinterpret_cast<float2*>(smem);
         for (int i = tid; i < S::BLOB; i += NT) sm[i] = p.blob[i];
+        if (PRUNABLE && tid < S::RLAST) sm[OFF_G + tid] = cis_cycles(-(double)tid / (double)S::RLAST);
     }
 
     template <int PH>
@@ -210,8 +254,13 @@ template <class S, int RPC, int MODE> struct KRow {
             constexpr int NLINE = (int)((size_t)RPC * S::L * sizeof(float2) / 128);
             for (int l = tid; l < NLINE; l += NTA) prefetch_l2(a + (size_t)l * 128);
         }
-        if (S::NSTAGE == 3 && PH == 1) dif_stage_mid<S>(j, r.v, sm, acc);
-        if (S::NSTAGE >= 2 && PH == S::NSTAGE - 1) {
+        if (PRUNABLE && p.k1mask != 0u) {
+            if constexpr (PRUNABLE) {
+                if (PH == 1) dif_stage_mid_pruned<S>(j, r.v, sm, acc, p.k1mask);
+                if (PH == 2) pruned_last(p, wk, j, r, acc, gtab);
+            }
+        } else if (S::NSTAGE == 3 && PH == 1) dif_stage_mid<S>(j, r.v, sm, acc);
+        if (S::NSTAGE >= 2 && PH == S::NSTAGE - 1 && !(PRUNABLE && p.k1mask != 0u)) {
             // estimator modes: a thread whose last-stage outputs all fall outside the window (most of them: the
             // window is a few dozen of the L bins of a row) skips its last butterfly; whole warps drop out
             bool need = true;

@@ -345,6 +345,18 @@ public:
             if (r.ob1 > N2 - 1) r.ob1 = N2 - 1;
         }
         r.nlanes = lanes;
+        // output-pruned row pass (k_row.cuh PRUNABLE): which middle-stage outputs k1 feed a bin of those k2 ranges
+        r.k1mask = 0u;
+        if (RS::NSTAGE == 3 && RS::R0 == 20 && RS::R1 == 20 && RS::R2 == 20 && RPC == 1 && !getenv("TWSTFT_NO_PRUNE")) {
+            unsigned mask = 0u;
+            long long nout = 0;
+            const int lo[2] = {r.oa1, r.oa2}, hi[2] = {r.ob1, r.ob2};
+            for (int g = 0; g < 2; g++)
+                for (int o = lo[g]; o <= hi[g]; o++) { mask |= 1u << ((o % RS::NSLAST) / RS::R0); nout++; }
+            int bits = 0;
+            for (int b = 0; b < 20; b++) bits += (mask >> b) & 1u;
+            if (bits > 0 && bits <= 8 && nout <= 2 * RS::NTS) r.k1mask = mask;       // wide windows: the full transform
+        }
         return r;
     }
 

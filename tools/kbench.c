@@ -8,7 +8,9 @@
  *
  * Development tool only (not part of the product path, not a benchmark of record: bench.py is).
  */
+#define _POSIX_C_SOURCE 200809L
 #include <dlfcn.h>
+#include <time.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -25,12 +27,23 @@ static inline double uni(void) { return ((rng() >> 11) + 0.5) * (1.0 / 900719925
 
 static int16_t sat16(double v) { v = rint(v); if (v > 32767) v = 32767; if (v < -32768) v = -32768; return (int16_t)v; }
 
+/* dual-plan experiment: two plans on the same GPU driven by two host threads, each over half the records */
+#include <pthread.h>
+typedef struct { int (*proc)(twstft_plan*, const int16_t*, size_t, twstft_result*); twstft_plan* plan; const int16_t* dev; size_t n; twstft_result* res; int steps; } job;
+static void* job_main(void* a)
+{
+    job* j = (job*)a;
+    for (int s = 0; s < j->steps; s++) j->proc(j->plan, j->dev, j->n, j->res);
+    return NULL;
+}
+
 int main(int argc, char** argv)
 {
     if (argc < 2) { fprintf(stderr, "usage: kbench lib.so [R] [steps] [fast] [distinct] [snr_db]\n"); return 2; }
     const int R = argc > 2 ? atoi(argv[2]) : 16, steps = argc > 3 ? atoi(argv[3]) : 6;
     const int fast = argc > 4 ? atoi(argv[4]) : 1, distinct = argc > 5 ? atoi(argv[5]) : 4;
     const double snr_db = argc > 6 ? atof(argv[6]) : -5.0;
+    const int dual = argc > 7 ? atoi(argv[7]) : 0;
     void* h = dlopen(argv[1], RTLD_NOW | RTLD_LOCAL);
     if (!h) { fprintf(stderr, "dlopen: %s\n", dlerror()); return 2; }
     SYM(twstft_default_config) SYM(twstft_plan_create) SYM(twstft_plan_destroy) SYM(twstft_last_error)
@@ -90,6 +103,26 @@ int main(int argc, char** argv)
     float ms = 0;
     p_twstft_timer_stop(plan, &ms);
     const long long launches = p_twstft_kernel_launches(plan) - l0;
+    if (dual) {     /* second plan, same device: the two halves of the batch run concurrently on two streams */
+        twstft_plan* plan2 = NULL;
+        cfg.max_batch = R / 2;
+        if (p_twstft_plan_create(&cfg, &plan2) || p_twstft_gen_code(plan2, 22, 3, 0, 1, N / 2, chips)) { fprintf(stderr, "plan2 failed\n"); return 1; }
+        twstft_result* res2 = (twstft_result*)calloc((size_t)R, sizeof(twstft_result));
+        job jb[2] = {{p_twstft_process_device, plan, (const int16_t*)dev, (size_t)R / 2, res, 3},
+                     {p_twstft_process_device, plan2, (const int16_t*)((char*)dev + (size_t)(R / 2) * rec_i16 * 2), (size_t)R / 2, res2, 3}};
+        pthread_t th[2];
+        for (int t = 0; t < 2; t++) pthread_create(&th[t], NULL, job_main, &jb[t]);
+        for (int t = 0; t < 2; t++) pthread_join(th[t], NULL);
+        jb[0].steps = jb[1].steps = steps;
+        struct timespec a, b;
+        clock_gettime(CLOCK_MONOTONIC, &a);
+        for (int t = 0; t < 2; t++) pthread_create(&th[t], NULL, job_main, &jb[t]);
+        for (int t = 0; t < 2; t++) pthread_join(th[t], NULL);
+        clock_gettime(CLOCK_MONOTONIC, &b);
+        const double dt = (b.tv_sec - a.tv_sec) + 1e-9 * (b.tv_nsec - a.tv_nsec);
+        printf("{\"dual_plans\": true, \"R\": %d, \"ms_per_step_wall\": %.4f, \"records_per_s\": %.1f}\n", R, 1e3 * dt / steps, R * steps / dt);
+        p_twstft_plan_destroy(plan2);
+    }
     p_twstft_profile_enable(plan, 1);
     for (int s = 0; s < 2; s++) p_twstft_process_device(plan, (const int16_t*)dev, R, res);
     p_twstft_profile_enable(plan, 0);
