@@ -89,6 +89,7 @@ public:
     u64 *d_keyrow = nullptr, *d_keycol = nullptr;
     i64 *d_sbin = nullptr, *d_p0 = nullptr;
     float2 *d_y0 = nullptr, *d_lrow = nullptr, *d_lcol = nullptr;
+    float2 *d_lrow2 = nullptr, *d_lcol2 = nullptr;     // W_2N^n tables of the 2N-sample block estimator (block2_passes)
     static constexpr int NROWBLK = L1 / RPC;
     static constexpr int NCOLTILE = N2 / TS;
     static constexpr int NCOLTILE_I = N2 / TSI;
@@ -99,7 +100,7 @@ public:
         void* all[] = {d_blob_c, d_blob_r, d_code, d_qconst, d_A, d_B, d_sums, d_energy, d_df, d_peakpart,
                        d_keyrow, d_keycol, d_sbin, d_p0, d_y0, d_lrow, d_lcol, d_stat, d_bankpart, d_ang, d_finepart,
                        d_code_win, d_P, d_R2, d_U2, d_keycol2, d_fn, d_fbase, d_fa2, d_ffail, d_penergy, d_spart,
-                       d_lagpart, d_hbtab, d_fwork, d_ftiles, d_fk1};
+                       d_lagpart, d_hbtab, d_fwork, d_ftiles, d_fk1, d_lrow2, d_lcol2};
         for (void* p : all) be->free(p);
     }
     i64 size() const override { return N; }
@@ -295,6 +296,7 @@ public:
         c.half_stride = half_stride;
         c.src = a.d_raw; c.dst = d_A; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.invN = 1.0 / (double)N; c.nch = a.nch;
         c.sub_mean = sub_mean; c.sums = d_sums; c.lrow = d_lrow; c.lcol = d_lcol;
+        if (OP >= 10) { c.lrow = d_lrow2; c.lcol = d_lcol2; }        // radix-2 split of a 2N block: the plan's W_2N^n tables
         c.rec_stride = a.rec_stride; c.rec_offset = a.d_rec_offset; c.nq = 1;
         c.ntx = NCOLTILE * a.nch; c.ny = a.nrec;
         if (a.d_cf) {
@@ -378,13 +380,19 @@ public:
         const int lanes = a.nrec * a.nch;
         if (lanes > max_lanes) return -2;
         have_means = false;
-        {   // W_2N^n = exp(-2 pi i n/(2N)) as a "derotation" by fs/(2N) through the two-level tables
-            std::vector<double> half(lanes, a.fs / (2.0 * (double)N));
-            be->h2d(d_df, half.data(), sizeof(double) * lanes);
+        if (!d_lrow2) {   // W_2N^n = exp(-2 pi i n/(2N)) as a "derotation" by fs/(2N) through the two-level tables: the same
+            // for every lane and every call, built once per plan (it used to cost a blocking copy and a launch per block)
+            d_lrow2 = dalloc<float2>((size_t)max_lanes * L1);
+            d_lcol2 = dalloc<float2>((size_t)max_lanes * N2);
+            if (!d_lrow2 || !d_lcol2 || !be->ok()) return -1;
+            std::vector<double> half(max_lanes, a.fs / (2.0 * (double)N));
+            be->h2d(d_df, half.data(), sizeof(double) * max_lanes);
             be->sync();
-            RunArgs t = a;
-            t.d_df_in = d_df;
-            df_final(t, nullptr);
+            DfParams d{};
+            d.part_key = d_keyrow; d.npart = NROWBLK; d.key_stride = 2 * NROWBLK; d.df_in = d_df; d.power = 1.0; d.naxis = 0;
+            d.fs = a.fs; d.L1 = L1; d.N2 = N2; d.df_out = d_df; d.s_out = d_sbin; d.lrow = d_lrow2; d.lcol = d_lcol2;
+            d.nsplit = 8;
+            be->template launch<KDfFinal>(dim3(d.nsplit, max_lanes, 1), d);
         }
         typedef KRow<RS, RPC, MODE> KR;
         for (int par = 0; par < 2; par++) {
