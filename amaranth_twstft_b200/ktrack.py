@@ -33,6 +33,9 @@ process_file returns None when no block holds the carrier.
 
 processing/C/claudio_aligned.c is the same front end in C (the production binary); this module is the Python
 mirror the parity tests drive.
+
+The C program processing/C/claudio_aligned.c is the authoritative implementation of this loop; this Python mirror over the same
+C ABI exists so that the parity tests can drive the loop step by step.
 """
 import numpy as np
 

@@ -2,7 +2,10 @@
 
 Mirrors acquisition/go_1s.m: validity selection (:80-87), conversion of (indice1, correction1) to nanoseconds
 (:88-90), and the `.1s` file -- one row per second, each value the 25-point linear fit of the 25 window delays
-of that second evaluated at its 13th point (:251-266).  Two-way combination and plots stay in the scripts."""
+of that second evaluated at its 13th point (:251-266).  Two-way combination and plots stay in the scripts.
+The C program processing/C/go_1s.c is the authoritative implementation of this loop; this Python mirror over the same
+C ABI exists so that the parity tests can drive the loop step by step.
+"""
 import numpy as np
 
 HEADER = "# MJD\t\tOPlocal\tOPremote\tLTFBlocal\tLTBBremote\n"          # go_1s.m:253 (typo kept: file format)

@@ -9,6 +9,7 @@ import pytest
 
 import parity_common as pc
 from amaranth_twstft_b200 import shard, synth
+from dist_gather import gather_results
 from amaranth_twstft_b200.api import Correlator
 
 pytestmark = pytest.mark.skipif(not os.path.exists(pc.EMU_LIB), reason="emulation library not built")
@@ -38,7 +39,7 @@ def _worker(rank, world, port, q):
     with Correlator(nsamples=N, max_batch=2, lib=pc.EMU_LIB) as cor:
         cor.set_code(bits)
         lo, local = shard.process_shard(cor, lambda a, b: recs[a:b], NREC, rank, world)
-    full = shard.gather_results(local, NREC, 2, rank, world)
+    full = gather_results(local, NREC, 2, rank, world)
     if rank == 0:
         q.put(full)
     dist.barrier()
