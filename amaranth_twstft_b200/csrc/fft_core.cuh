@@ -211,8 +211,11 @@ template <class S, class Acc> HD void dif_stage_mid(int j, float2* v, const floa
 // carrier window, i.e. a handful of (k0 + 20 k1) groups: the five radix-4 butterflies of the first PFA half are
 // shared, each wanted output then costs one five-term dot product with constant roots instead of its share of four
 // radix-5 butterflies, 19 twiddles and 20 stores.  The mask is uniform over the CTA (no divergence).
-template <class S, class Acc> HD void dif_stage_mid_pruned(int j, float2* v, const float2* tw, const Acc& acc, unsigned mask)
+// CMASK != 0: the mask is known at compile time (the default carrier window of the 1-s records), no tests remain.
+template <class S, class Acc, unsigned CMASK = 0u>
+HD void dif_stage_mid_pruned(int j, float2* v, const float2* tw, const Acc& acc, unsigned mask_rt)
 {
+    const unsigned mask = CMASK ? CMASK : mask_rt;
     static_assert(S::R1 == 20 && S::SD1::B == S::R1, "pruned middle stage: radix 20, every twiddle power tabulated");
     static_assert((S::L / S::R1) / S::NTS == 1, "one middle-stage butterfly per thread");
     int k0, i2;

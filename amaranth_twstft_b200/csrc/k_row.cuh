@@ -256,7 +256,11 @@ template <class S, int RPC, int MODE> struct KRow {
         }
         if (PRUNABLE && p.k1mask != 0u) {
             if constexpr (PRUNABLE) {
-                if (PH == 1) dif_stage_mid_pruned<S>(j, r.v, sm, acc, p.k1mask);
+                if (PH == 1) {
+                    constexpr unsigned LOCAL = 0xC0003u;       // k1 = 0, 1, 18, 19: |f| < 20 kHz on the 625 x 8000 split
+                    if (p.k1mask == LOCAL) dif_stage_mid_pruned<S, Acc, LOCAL>(j, r.v, sm, acc, LOCAL);
+                    else dif_stage_mid_pruned<S, Acc>(j, r.v, sm, acc, p.k1mask);
+                }
                 if (PH == 2) pruned_last(p, wk, j, r, acc, gtab);
             }
         } else if (S::NSTAGE == 3 && PH == 1) dif_stage_mid<S>(j, r.v, sm, acc);
