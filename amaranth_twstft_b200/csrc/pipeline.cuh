@@ -112,6 +112,16 @@ public:
 
     // persistent kernels: one wave of resident CTAs, each looping over work items
     bool persistent = false;   // false: one CTA per work item; true: one resident wave looping over items
+    // estimator row passes: a few resident waves, each CTA looping over ~a dozen rows and pulling its next row towards
+    // L2 while it transforms the current one (measured: 8 waves -4 % against one CTA per row, one wave +0 %)
+    template <class K> dim3 rgrid(i64 total) const
+    {
+        i64 g = (i64)be->num_sms * K::MINB * 8;
+        if (persistent) g = (i64)be->num_sms * K::MINB;
+        if (g > total) g = total;
+        if (g < 1) g = 1;
+        return dim3((unsigned)g, 1, 1);
+    }
     template <class K> dim3 pgrid(i64 total) const
     {
         i64 g = persistent ? (i64)be->num_sms * K::MINB : total;
@@ -401,7 +411,7 @@ public:
             RowParams r = estimator_row(a, e, 2, par, 2 * N);
             r.key_off = par * NROWBLK;
             r.winmag = d_win;
-            be->template launch<KR>(pgrid<KR>((i64)NROWBLK * lanes), r);
+            be->template launch<KR>(rgrid<KR>((i64)NROWBLK * lanes), r);
         }
         return 0;
     }
@@ -427,7 +437,7 @@ public:
         if (lanes > max_lanes) return -2;
         RowParams r = estimator_front(a, e);
         typedef KRow<RS, RPC, ROW_FWD_ARGMAX> KR;
-        be->template launch<KR>(pgrid<KR>((i64)NROWBLK * lanes), r);
+        be->template launch<KR>(rgrid<KR>((i64)NROWBLK * lanes), r);
         df_final(a, &e);
         return be->ok() ? 0 : -1;
     }
@@ -477,7 +487,7 @@ public:
         have_means = false;
         r.winmag = d_win;
         typedef KRow<RS, RPC, ROW_FWD_WINMAG> KR;
-        be->template launch<KR>(pgrid<KR>((i64)NROWBLK * lanes), r);
+        be->template launch<KR>(rgrid<KR>((i64)NROWBLK * lanes), r);
         return be->ok() ? 0 : -1;
     }
 
