@@ -90,6 +90,7 @@ struct RowCorrParams {
     int conj_mode;           // 0: Y*conj(C) (variant G)   1: conj(Y)*C (variant K)
     double* part_energy;     // [lane][nblk]  sum |Y|^2
     float2* y0;              // [lane] Y[0]
+    int* counter;            // dynamic work distribution (launch.cuh): zeroed by the host before the launch
     float2* pdst;            // optional [lane][N1][L]: the product spectrum P (fast peak path, k_fast.cuh)
     double* part_penergy;    // with pdst: [lane][nblk] sum |P|^2
 };
@@ -139,7 +140,7 @@ template <class S, int RPC, int NQ> struct KRowCorr {
         double dsum[NSUM];
         unsigned tmem;       // TMEM base address of this CTA (device)
         float2 obase[(S::L / S::RLAST) / S::NTS];   // four-step twiddle base of this thread's outputs, per item
-        int crow;            // CODE_TMEM: row whose code values sit in this thread's TMEM window (-1: none)
+        int crow = -1;       // CODE_TMEM: row whose code values sit in this thread's TMEM window (-1: none)
 #ifdef TWSTFT_EMU
         float2 P[S::E];      // host emulation: the parked spectrum / code row
 #endif
@@ -151,20 +152,19 @@ template <class S, int RPC, int NQ> struct KRowCorr {
     static HD constexpr int sync_after(int ph) { return ph == NST - 1 ? SYNC_SUMD : SYNC_BARRIER; }
 
     // work item w = (rowblk = w / nlanes, lane = w % nlanes): CTAs that run together share the code row in L2
-    static HD int niter(const Params& p, int bx, int gdim)
-    {
-        const i64 total = (i64)p.nblk * p.nlanes;
-        if (CODE_TMEM) {     // contiguous run of items per CTA
-            const i64 per = (total + gdim - 1) / gdim, start = (i64)bx * per;
-            return start < total ? (int)(total - start < per ? total - start : per) : 0;
-        }
-        return bx < total ? (int)((total - bx + gdim - 1) / gdim) : 0;
-    }
+#ifndef TWSTFT_ROWCORR_DYNAMIC
+#define TWSTFT_ROWCORR_DYNAMIC 1
+#endif
+    // items in (row, lane) order; a CTA grabs CHUNK consecutive ones at a time (launch.cuh, dynamic distribution): the
+    // lanes of one row stay together, so the code row in tensor memory is re-read once per chunk at most
+    static constexpr int CHUNK = 8;
+    static HD int total_items(const Params& p) { return p.nblk * p.nlanes; }
+    static HD int* counter(const Params& p) { return p.counter; }
+    static HD int niter(const Params&, int, int) { return 0; }
     struct Work { int rowblk; i64 lane; };
-    static HD Work work_of(const Params& p, const Blk& blk, int it)
+    static HD Work work_of(const Params& p, const Blk&, int it)
     {
-        const i64 total = (i64)p.nblk * p.nlanes;
-        const i64 w = CODE_TMEM ? (i64)blk.x * ((total + blk.gx - 1) / blk.gx) + it : (i64)blk.x + (i64)it * blk.gx;
+        const i64 w = it;
         Work k;
         k.rowblk = (int)(w / p.nlanes);
         k.lane = w % p.nlanes;
@@ -230,7 +230,6 @@ template <class S, int RPC, int NQ> struct KRowCorr {
             r.dsum[0] = 0.0;
             if (PSTORE) r.dsum[NSUM - 1] = 0.0;
             if (CODE_TMEM) {
-                if (it == 0) r.crow = -1;
                 if (r.crow != row) {                      // uniform over the CTA's rows: every thread of a warp takes part
                     if (active) {
                         const float2* c = p.code + (i64)row * S::L + j;

@@ -121,6 +121,13 @@ template <class K> struct TmemCols<K, decltype((void)K::TMEM_COLS)> { static con
 template <class K, class = void> struct HasPrologue { static constexpr bool value = false; };
 template <class K> struct HasPrologue<K, decltype((void)&K::prologue)> { static constexpr bool value = true; };
 
+// Resident kernels with DYNAMIC work distribution declare K::CHUNK (items per grab), K::total_items(p) and
+// K::counter(p) (a device int the host zeroes before the launch): a CTA takes the next CHUNK items with one atomicAdd
+// and `it` is then the GLOBAL item index.  SMs do not run at the same speed (L2 distance, co-resident CTAs), so a
+// static split of the items makes every launch as slow as its slowest SM.
+template <class K, class = void> struct IsDynamic { static constexpr bool value = false; };
+template <class K> struct IsDynamic<K, decltype((void)K::CHUNK)> { static constexpr bool value = true; };
+
 template <class K> __global__ void __launch_bounds__(K::NT, K::MINB) kernel_entry(const typename K::Params p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -143,7 +150,22 @@ template <class K> __global__ void __launch_bounds__(K::NT, K::MINB) kernel_entr
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         r.tmem = tmem_slot;
     }
-    if constexpr (K::PERSISTENT) {
+    if constexpr (IsDynamic<K>::value) {
+        __shared__ int s_base;
+        const int total = K::total_items(p);
+        for (;;) {
+            __syncthreads();                 // the previous chunk is done: s_base and the shared buffers are free
+            if (threadIdx.x == 0) s_base = atomicAdd(K::counter(p), (int)K::CHUNK);
+            __syncthreads();
+            const int base = s_base;
+            if (base >= total) break;
+            const int end = base + K::CHUNK < total ? base + K::CHUNK : total;
+            for (int it = base; it < end; it++) {
+                if (it > base) __syncthreads();
+                run_phases<K, 0>(p, b, (int)threadIdx.x, r, smem, it, end);
+            }
+        }
+    } else if constexpr (K::PERSISTENT) {
         const int nit = K::niter(p, (int)blockIdx.x, (int)gridDim.x);
         for (int it = 0; it < nit; it++) {
             if (it > 0) __syncthreads();     // shared buffers of the previous item are free again

@@ -87,6 +87,7 @@ public:
     float2 *d_A = nullptr, *d_B = nullptr;
     double *d_sums = nullptr, *d_energy = nullptr, *d_df = nullptr, *d_peakpart = nullptr, *d_stat = nullptr, *d_bankpart = nullptr;
     u64 *d_keyrow = nullptr, *d_keycol = nullptr;
+    int* d_counter = nullptr;  // work counter of the dynamically scheduled kernels
     i64 *d_sbin = nullptr, *d_p0 = nullptr;
     float2 *d_y0 = nullptr, *d_lrow = nullptr, *d_lcol = nullptr;
     float2 *d_lrow2 = nullptr, *d_lcol2 = nullptr;     // W_2N^n tables of the 2N-sample block estimator (block2_passes)
@@ -97,7 +98,7 @@ public:
     ~Pipe() override
     {
         if (!be) return;
-        void* all[] = {d_blob_c, d_blob_r, d_code, d_qconst, d_A, d_B, d_sums, d_energy, d_df, d_peakpart,
+        void* all[] = {d_counter, d_blob_c, d_blob_r, d_code, d_qconst, d_A, d_B, d_sums, d_energy, d_df, d_peakpart,
                        d_keyrow, d_keycol, d_sbin, d_p0, d_y0, d_lrow, d_lcol, d_stat, d_bankpart, d_ang, d_finepart,
                        d_code_win, d_P, d_R2, d_U2, d_keycol2, d_fn, d_fbase, d_fa2, d_ffail, d_penergy, d_spart,
                        d_lagpart, d_hbtab, d_fwork, d_ftiles, d_fk1, d_lrow2, d_lcol2};
@@ -169,6 +170,7 @@ public:
         d_stat = dalloc<double>((size_t)lanes * NCOLTILE_I * 2);
         d_bankpart = dalloc<double>((size_t)lanes * 2 * BANK_NPTS);
         d_keyrow = dalloc<u64>((size_t)lanes * NROWBLK * 2);
+        d_counter = dalloc<int>(4);
         d_keycol = dalloc<u64>((size_t)lanes * nq * NCOLTILE_I);
         d_sbin = dalloc<i64>(lanes);
         d_p0 = dalloc<i64>(lanes);
@@ -508,6 +510,7 @@ public:
         typedef KRowCorr<RS, RPC, 1> K1;
         i64 g = (i64)NROWBLK * lanes;
         if (g > (i64)be->num_sms * K1::MINB) g = (i64)be->num_sms * K1::MINB;
+        be->zero(d_counter, sizeof(int)); r.counter = d_counter;
         be->template launch<K1>(dim3((unsigned)g, 1, 1), r);
         ColParams c{};
         c.src = d_B; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.invN = 1.0 / (double)N; c.nch = 1; c.nq = 1;
@@ -545,6 +548,7 @@ public:
             typedef KRowCorr<RS, RPC, 1> K1;
             const i64 wave = (i64)be->num_sms * K3::MINB;      // resident CTAs: TMEM columns are per CTA
             if (g > wave) g = wave;
+            be->zero(d_counter, sizeof(int)); r.counter = d_counter;
             if (nq == 3) be->template launch<K3>(dim3((unsigned)g, 1, 1), r);
             else be->template launch<K1>(dim3((unsigned)g, 1, 1), r);
         };
@@ -585,6 +589,7 @@ public:
         r.pdst = d_P; r.part_penergy = d_penergy;
         i64 g = (i64)NROWBLK * lanes;
         if (g > (i64)be->num_sms * K1::MINB) g = (i64)be->num_sms * K1::MINB;
+        be->zero(d_counter, sizeof(int)); r.counter = d_counter;
         be->template launch<K1>(dim3((unsigned)g, 1, 1), r);
         ColParams c{};
         c.src = d_B; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.invN = 1.0 / (double)N; c.nch = 1; c.nq = 1;

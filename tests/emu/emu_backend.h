@@ -80,7 +80,16 @@ struct Backend {
                     Blk b{(int)x, (int)y, (int)z, (int)grid.x};
                     if constexpr (HasPrologue<K>::value)
                         for (int tid = 0; tid < K::NT; tid++) K::prologue(p, tid, smem.data());
-                    if constexpr (K::PERSISTENT) {
+                    if constexpr (IsDynamic<K>::value) {
+                        // dynamic work distribution: on the host the chunks are dealt out to the CTAs in turn
+                        const int total = K::total_items(p);
+                        int k = 0;
+                        for (int base = 0; base < total; base += K::CHUNK, k++) {
+                            if (k % (int)grid.x != (int)x) continue;
+                            const int end = base + K::CHUNK < total ? base + K::CHUNK : total;
+                            for (int it = base; it < end; it++) EmuPhases<K, 0>::run(p, b, regs, smem.data(), it, end);
+                        }
+                    } else if constexpr (K::PERSISTENT) {
                         const int nit = K::niter(p, (int)x, (int)grid.x);
                         for (int it = 0; it < nit; it++) EmuPhases<K, 0>::run(p, b, regs, smem.data(), it, nit);
                     } else {
