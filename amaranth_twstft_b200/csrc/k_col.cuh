@@ -15,6 +15,10 @@
 #pragma once
 #include "fft_core.cuh"
 
+#ifndef TWSTFT_ABLATE
+#define TWSTFT_ABLATE 0      // timing experiments only (results are wrong), bit mask: 1 no stores, 2 no loads, 4 no butterflies
+#endif
+
 namespace twstft {
 
 enum ColSrc { SRC_RAW = 0, SRC_CF32 = 1, SRC_BITS = 2 };
@@ -54,6 +58,7 @@ struct ColParams {
     double* part_stat;     // COL_INV_ARGMAX_STATS: [y][ntx][2]  sum|z|, sum|z|^2 of the tile
     u64* part_key2;        // COL_INV_ARGMAX_K2: [y][ntx]
     const int* tile_list;  // COL_INV_ARGMAX_K2, optional: [y][ntx] column tile of work item (x, y) (a few tiles per lane)
+    int pf_dist;           // > 0: every CTA pulls the rows of work item (its own + pf_dist) towards L2 before it starts
 };
 
 // N2C / NCH: row length and channel count as compile-time constants (0 = take them from Params), so that
@@ -68,6 +73,7 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
              : SRC == SRC_RAW ? "col_fwd_raw" : SRC == SRC_BITS ? "col_fwd_bits" : OP != 0 ? "col_fwd_cf32_op" : "col_fwd_cf32";
     }
     static constexpr bool PERSISTENT = true;
+    static constexpr bool INVERSE = (MODE != COL_FWD);
     static constexpr int NTA = S::NTS * TS;
     static constexpr int NT = (NTA + 31) / 32 * 32;
     static constexpr int MINB = (S::L * TS >= 8000) ? 2 : 4;
@@ -116,6 +122,23 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
         return k;
     }
 
+    // Column s of tile `tile` -> (channel, n2, element offset inside a raw row).  Interleaved two-channel records
+    // (CHSPLIT): a tile holds TS sample instants of ONE channel (even tiles channel 0, odd tiles channel 1), so that the
+    // stores of a row are full TS*8-byte runs; the two CTAs of a pair read the same raw sectors (the second from L2).
+#ifndef TWSTFT_CHSPLIT
+#define TWSTFT_CHSPLIT 1
+#endif
+    static constexpr bool CHSPLIT = (TWSTFT_CHSPLIT != 0) && SRC == SRC_RAW && NCH == 2;
+    struct ColIdx { int ch, n2, rawcol; };
+    static HD ColIdx colidx(const Params& p, int tile, int s)
+    {
+        ColIdx c;
+        if (SRC != SRC_RAW) { c.ch = 0; c.n2 = tile * TS + s; c.rawcol = c.n2; }
+        else if (CHSPLIT) { c.ch = tile & 1; c.n2 = (tile >> 1) * TS + s; c.rawcol = c.n2 * 2 + c.ch; }
+        else { const int col = tile * TS + s; c.ch = col % nchof(p); c.n2 = col / nchof(p); c.rawcol = col; }
+        return c;
+    }
+
     static constexpr int POW = OP % 10;                 // 1 derotate, 2 / 4 power
     static constexpr int SPLIT = OP / 10;               // 0 none, 1 even half-sum, 2 odd half-difference
     static constexpr bool USE_LROW = (OP == 1 || SPLIT == 2);
@@ -137,9 +160,10 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
     // with the int16 unpack / mean removal / pre-transform operation fused in
     static HD void load0(const Params& p, const Work& wk, int s, int j, Regs& r)
     {
-        const int col = wk.tile * TS + s;
+        const ColIdx ci = colidx(p, wk.tile, s);
+        const int col = ci.rawcol;
         if (SRC == SRC_RAW) {
-            const i64 lane = (i64)wk.y * nchof(p) + col % nchof(p);
+            const i64 lane = (i64)wk.y * nchof(p) + ci.ch;
             float mx = 0.f, my = 0.f;
             if (p.sub_mean) {
                 mx = (float)(p.sums[lane * 2] * p.invN);
@@ -154,7 +178,8 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
             for (int b = 0; b < NB0; b++)
 #pragma unroll
                 for (int m = 0; m < S::R0; m++) {
-                    const short2 raw = gsrc[b * bstride + m * mstride];
+                    const short2 raw = ((TWSTFT_ABLATE & 2) && p.ny > 0) ? make_short2((short)(j + b), (short)(m + s))
+                                                                        : gsrc[b * bstride + m * mstride];
                     const float2 x = make_float2((float)raw.x - mx, (float)raw.y - my);
                     if (SPLIT == 0) {
                         r.v[b * S::R0 + m] = pre_op(x, OP == 1 ? lr[S::NTS * b + m * S::SP0] : x);
@@ -196,7 +221,8 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
             for (int b = 0; b < NB0; b++)
 #pragma unroll
                 for (int m = 0; m < S::R0; m++) {
-                    const float2 x = gsrc[b * bstride + m * mstride];
+                    const float2 x = ((TWSTFT_ABLATE & 2) && p.ny > 0) ? make_float2((float)(j + b), (float)(m + s))
+                                                                      : gsrc[b * bstride + m * mstride];
                     r.v[b * S::R0 + m] = (MODE == COL_FWD) ? x : cswap(x);
                 }
         } else {  // SRC_BITS: sample n = n1*N2 + col holds chip n/rep
@@ -214,11 +240,32 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
         }
     }
 
+    // The CTA that will run work item w2 starts about one resident wave after this one: its TS-element row pieces
+    // (L of them, a row apart) are requested now so that its stage-0 loads find them in L2.
+    static HD void prefetch_item(const Params& p, i64 w2, int tid)
+    {
+        if (w2 >= (i64)p.ntx * p.ny) return;
+        const int x2 = (int)(w2 % p.ntx), y2 = (int)(w2 / p.ntx);
+        const char* base;
+        size_t rstride;
+        constexpr size_t ELEM = (SRC == SRC_RAW) ? sizeof(short2) : sizeof(float2);
+        if (SRC == SRC_RAW || (SRC == SRC_CF32 && MODE == COL_FWD && OP != 0)) {
+            const int nch = (SRC == SRC_RAW) ? nchof(p) : 1;
+            const i64 rbase = p.rec_offset ? p.rec_offset[y2] : (i64)y2 * p.rec_stride;
+            base = reinterpret_cast<const char*>(p.src) + (size_t)(rbase + (i64)(CHSPLIT ? (x2 >> 1) * 2 : x2) * TS) * ELEM;
+            rstride = (size_t)nch * n2of(p) * ELEM;
+        } else {
+            base = reinterpret_cast<const char*>(p.src) + (size_t)((i64)y2 * p.N + (i64)x2 * TS) * ELEM;
+            rstride = (size_t)n2of(p) * ELEM;
+        }
+        constexpr int PER = (int)(((CHSPLIT ? 2 : 1) * TS * ELEM + 127) / 128);
+        for (int l = tid; l < S::L * PER; l += NTA) prefetch_l2(base + (size_t)(l / PER) * rstride + (size_t)(l % PER) * 128);
+    }
+
     static HD void epilogue(const Params& p, const Work& wk, int s, int j, Regs& r, const float2* g)
     {
-        const int col = wk.tile * TS + s;
-        const int ch = (SRC == SRC_RAW) ? col % nchof(p) : 0;
-        const int n2 = (SRC == SRC_RAW) ? col / nchof(p) : col;
+        const ColIdx ci = colidx(p, wk.tile, s);
+        const int ch = ci.ch, n2 = ci.n2;
         if (MODE == COL_FWD) {
             const i64 lane = (SRC == SRC_RAW) ? (i64)wk.y * nchof(p) + ch : (i64)wk.y;
             float2* d = p.dst + lane * p.N + n2;
@@ -231,9 +278,13 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
             }
             const i64 bstr = (i64)S::NTS * n2of(p), mstr = (i64)S::NSLAST * n2of(p);
             float2* dj = d + (i64)j * n2of(p);
+            float2 ablsum = make_float2(0.f, 0.f);
             last_stage_visit<S>(j, r.v, [&](int, float2 x, int b, int m) {
-                dj[b * bstr + m * mstr] = cmul(x, cmul(base[b], g[m * TS + s]));
+                const float2 y = cmul(x, cmul(base[b], g[m * TS + s]));
+                if (TWSTFT_ABLATE & 1) ablsum = cadd(ablsum, y);     // experiment: one store per thread instead of 25
+                else dj[b * bstr + m * mstr] = y;
             });
+            if (TWSTFT_ABLATE & 1) dj[0] = ablsum;
         } else if (MODE == COL_INV_STORE) {
             float2* dj = p.dst + (i64)wk.y * p.N + n2 + (i64)j * n2of(p);
             const i64 bstr = (i64)S::NTS * n2of(p), mstr = (i64)S::NSLAST * n2of(p);
@@ -279,23 +330,23 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
         if (PH == 0) {
             r.key = 0;
             for (int i = 0; i < NSUM; i++) r.dsum[i] = 0.0;
+            if (p.pf_dist > 0 && !K2 && SRC != SRC_BITS) prefetch_item(p, (i64)blk.x + (i64)it * blk.gx + p.pf_dist, tid);
             if (MODE == COL_FWD) {
                 for (int t = tid; t < NG; t += NTA) {
                     const int s2 = t % TS, m = t / TS;
-                    const int col2 = wk.tile * TS + s2;
-                    const i64 n2b = (SRC == SRC_RAW) ? col2 / nchof(p) : col2;
+                    const i64 n2b = colidx(p, wk.tile, s2).n2;
                     gtab[m * TS + s2] = cis_cycles(-(double)(n2b * S::NSLAST * m) * p.invN);
                 }
             }
         }
         if (PH == (S::NSTAGE == 1 ? 1 : 0)) {
             load0(p, wk, s, j, r);
-            dif_stage0<S>(j, r.v, sm, acc);
+            if (!(TWSTFT_ABLATE & 4) || p.ny < 0) dif_stage0<S>(j, r.v, sm, acc);
             if (S::NSTAGE == 1) epilogue(p, wk, s, j, r, gtab);
         }
         if (S::NSTAGE == 3 && PH == 1) dif_stage_mid<S>(j, r.v, sm, acc);
         if (S::NSTAGE >= 2 && PH == S::NSTAGE - 1) {
-            dif_stage_last<S>(j, r.v, acc);
+            if (!(TWSTFT_ABLATE & 4) || p.ny < 0) dif_stage_last<S>(j, r.v, acc);
             epilogue(p, wk, s, j, r, gtab);
         }
         if (K2 && PH == NCOMP) {

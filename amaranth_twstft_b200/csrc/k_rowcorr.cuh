@@ -16,6 +16,10 @@
 #pragma once
 #include "fft_core.cuh"
 
+#ifndef TWSTFT_ABLATE_RC
+#define TWSTFT_ABLATE_RC 0   // timing experiments only (results are wrong), bit mask: 1 one store per thread, 2 no loads of A
+#endif
+
 namespace twstft {
 
 // ---- TMEM park/fetch of a thread's E complex values (device) / plain array (test emulation) ----
@@ -157,7 +161,10 @@ template <class S, int RPC, int NQ> struct KRowCorr {
 #endif
     // items in (row, lane) order; a CTA grabs CHUNK consecutive ones at a time (launch.cuh, dynamic distribution): the
     // lanes of one row stay together, so the code row in tensor memory is re-read once per chunk at most
-    static constexpr int CHUNK = 8;
+#ifndef TWSTFT_ROWCORR_CHUNK
+#define TWSTFT_ROWCORR_CHUNK 8
+#endif
+    static constexpr int CHUNK = TWSTFT_ROWCORR_CHUNK;
     static HD int total_items(const Params& p) { return p.nblk * p.nlanes; }
     static HD int* counter(const Params& p) { return p.counter; }
     static HD int niter(const Params&, int, int) { return 0; }
@@ -252,7 +259,9 @@ template <class S, int RPC, int NQ> struct KRowCorr {
 #pragma unroll
                 for (int b = 0; b < NB0; b++)
 #pragma unroll
-                    for (int m = 0; m < S::R0; m++) r.v[b * S::R0 + m] = xj[S::NTS * b + m * S::SP0];
+                    for (int m = 0; m < S::R0; m++)
+                        r.v[b * S::R0 + m] = ((TWSTFT_ABLATE_RC & 2) && p.nlanes > 0) ? make_float2((float)(j + m), (float)(row - m))
+                                                                                    : xj[S::NTS * b + m * S::SP0];
                 dif_stage0<S>(j, r.v, sm, acc);
             }
         }
@@ -336,7 +345,11 @@ template <class S, int RPC, int NQ> struct KRowCorr {
                         e += cnorm(x);
                         const float2 pr = cm ? cmul(cconj(x), cc[i]) : cmulc(x, cc[i]);
                         r.v[el] = pr;
-                        if (PSTORE && pd) { pd[out_index(el)] = pr; e2 += cnorm(pr); }
+                        if (PSTORE && pd) {
+                            if (TWSTFT_ABLATE_RC & 1) { if (el == 0) pd[out_index(el)] = pr; }
+                            else pd[out_index(el)] = pr;
+                            e2 += cnorm(pr);
+                        }
                     }
                 }
             }
@@ -358,9 +371,13 @@ template <class S, int RPC, int NQ> struct KRowCorr {
                         for (int b = 0; b < NBL; b++)
                             r.obase[b] = cis_cycles((double)((i64)row * (j + S::NTS * b)) * p.invN);
                     }
+                    float2 ablsum = make_float2(0.f, 0.f);
                     last_stage_visit<S>(j, r.v, [&](int o, float2 x, int b, int m) {
-                        d[o] = cmul(cswap(x), cmul(r.obase[b], gr[m]));
+                        const float2 y = cmul(cswap(x), cmul(r.obase[b], gr[m]));
+                        if (TWSTFT_ABLATE_RC & 1) ablsum = cadd(ablsum, y);
+                        else d[o] = y;
                     });
+                    if (TWSTFT_ABLATE_RC & 1) d[j] = ablsum;
                 }
             }
         }

@@ -122,7 +122,7 @@ template <class K, class = void> struct HasPrologue { static constexpr bool valu
 template <class K> struct HasPrologue<K, decltype((void)&K::prologue)> { static constexpr bool value = true; };
 
 // Resident kernels with DYNAMIC work distribution declare K::CHUNK (items per grab), K::total_items(p) and
-// K::counter(p) (a device int the host zeroes before the launch): a CTA takes the next CHUNK items with one atomicAdd
+// K::counter(p) (two device ints, zero before the first launch; the kernel leaves them at zero): a CTA takes the next CHUNK items with one atomicAdd
 // and `it` is then the GLOBAL item index.  SMs do not run at the same speed (L2 distance, co-resident CTAs), so a
 // static split of the items makes every launch as slow as its slowest SM.
 template <class K, class = void> struct IsDynamic { static constexpr bool value = false; };
@@ -164,6 +164,13 @@ template <class K> __global__ void __launch_bounds__(K::NT, K::MINB) kernel_entr
                 if (it > base) __syncthreads();
                 run_phases<K, 0>(p, b, (int)threadIdx.x, r, smem, it, end);
             }
+        }
+        // counter[1] counts the CTAs that are done; the last one leaves both counters at zero for the next launch
+        // on this stream (no memset between launches)
+        if (threadIdx.x == 0) {
+            int* c = K::counter(p);
+            __threadfence();
+            if (atomicAdd(c + 1, 1) == (int)gridDim.x - 1) { c[0] = 0; c[1] = 0; }
         }
     } else if constexpr (K::PERSISTENT) {
         const int nit = K::niter(p, (int)blockIdx.x, (int)gridDim.x);

@@ -118,14 +118,24 @@ public:
     template <class K> dim3 rgrid(i64 total) const
     {
         i64 g = (i64)be->num_sms * K::MINB * 8;
-        if (persistent) g = (i64)be->num_sms * K::MINB;
+        if (persistent || IsDynamic<K>::value) g = (i64)be->num_sms * K::MINB;
         if (g > total) g = total;
         if (g < 1) g = 1;
         return dim3((unsigned)g, 1, 1);
     }
+    // column passes (one CTA per tile): every CTA pulls the tile of the CTA that starts one resident wave later towards
+    // L2.  Measured (tools/kbench, 16 records): inverse arg-max pass 0.382 -> 0.373 ms at one wave, worse at two or
+    // three; forward raw pass unchanged at one wave, worse beyond -> on for the inverse passes only.
+    int col_pf = -1;           // TWSTFT_COL_PF: waves for every column pass (experiments); -1: the defaults above
+    template <class K> int pf_dist() const
+    {
+        const int waves = col_pf >= 0 ? col_pf : (K::INVERSE ? 1 : 0);
+        return persistent ? 0 : waves * be->num_sms * K::MINB;
+    }
+    int col_items = 1;         // column passes: work items per CTA (1: one CTA per tile)
     template <class K> dim3 pgrid(i64 total) const
     {
-        i64 g = persistent ? (i64)be->num_sms * K::MINB : total;
+        i64 g = persistent ? (i64)be->num_sms * K::MINB : (total + col_items - 1) / col_items;
         if (g > total) g = total;
         if (g < 1) g = 1;
         return dim3((unsigned)g, 1, 1);
@@ -136,6 +146,8 @@ public:
         be = b;
         persistent = false;
         if (const char* e = getenv("TWSTFT_PERSISTENT")) persistent = atoi(e) != 0;
+        if (const char* e = getenv("TWSTFT_COL_PF")) col_pf = atoi(e);
+        if (const char* e = getenv("TWSTFT_COL_ITEMS")) col_items = atoi(e) > 0 ? atoi(e) : 1;
         max_lanes = lanes;
         nq = nq_;
         std::vector<float2> blob(CS::BLOB + RS::BLOB + 4);
@@ -171,6 +183,7 @@ public:
         d_bankpart = dalloc<double>((size_t)lanes * 2 * BANK_NPTS);
         d_keyrow = dalloc<u64>((size_t)lanes * NROWBLK * 2);
         d_counter = dalloc<int>(4);
+        if (d_counter) be->zero(d_counter, 4 * sizeof(int));
         d_keycol = dalloc<u64>((size_t)lanes * nq * NCOLTILE_I);
         d_sbin = dalloc<i64>(lanes);
         d_p0 = dalloc<i64>(lanes);
@@ -255,6 +268,7 @@ public:
         c.src = d_bits; c.dst = d_A; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.invN = 1.0 / (double)N; c.nch = 1;
         c.rep = rep; c.qpsk = qpsk; c.code_mean = mean; c.nq = 1; c.ntx = NCOLTILE; c.ny = 1;
         typedef KCol<CS, TS, SRC_BITS, COL_FWD, 0, N2, 1> KC;
+        c.pf_dist = pf_dist<KC>();
         be->template launch<KC>(pgrid<KC>(NCOLTILE), c);
         RowParams r{};
         r.src = d_A; r.dst = d_code; r.blob = d_blob_r; r.N = N; r.N1 = L1; r.invN = 1.0 / (double)N; r.invM = 1.0 / ((double)nq * (double)N); r.nblk = NROWBLK;
@@ -277,6 +291,7 @@ public:
         c.src = d_in; c.dst = d_A; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.invN = 1.0 / (double)N; c.nch = 1;
         c.nq = 1; c.ntx = NCOLTILE; c.ny = lanes;
         typedef KCol<CS, TS, SRC_CF32, COL_FWD, 0, N2, 1> KC;
+        c.pf_dist = pf_dist<KC>();
         be->template launch<KC>(pgrid<KC>((i64)NCOLTILE * lanes), c);
         RowParams r{};
         r.src = d_A; r.dst = d_out; r.blob = d_blob_r; r.N = N; r.N1 = L1; r.invN = 1.0 / (double)N;
@@ -314,12 +329,15 @@ public:
         if (a.d_cf) {
             c.src = a.d_cf; c.sub_mean = 0; c.nch = 1; c.ntx = NCOLTILE;
             typedef KCol<CS, TS, SRC_CF32, COL_FWD, OP, N2, 1> KC;
+            c.pf_dist = pf_dist<KC>();
             be->template launch<KC>(pgrid<KC>((i64)c.ntx * c.ny), c);
         } else if (a.nch == 2) {
             typedef KCol<CS, TS, SRC_RAW, COL_FWD, OP, N2, 2> KC;
+            c.pf_dist = pf_dist<KC>();
             be->template launch<KC>(pgrid<KC>((i64)c.ntx * c.ny), c);
         } else {
             typedef KCol<CS, TS, SRC_RAW, COL_FWD, OP, N2, 1> KC;
+            c.pf_dist = pf_dist<KC>();
             be->template launch<KC>(pgrid<KC>((i64)c.ntx * c.ny), c);
         }
     }
@@ -413,7 +431,8 @@ public:
             RowParams r = estimator_row(a, e, 2, par, 2 * N);
             r.key_off = par * NROWBLK;
             r.winmag = d_win;
-            be->template launch<KR>(rgrid<KR>((i64)NROWBLK * lanes), r);
+            r.counter = d_counter;
+        be->template launch<KR>(rgrid<KR>((i64)NROWBLK * lanes), r);
         }
         return 0;
     }
@@ -439,6 +458,7 @@ public:
         if (lanes > max_lanes) return -2;
         RowParams r = estimator_front(a, e);
         typedef KRow<RS, RPC, ROW_FWD_ARGMAX> KR;
+        r.counter = d_counter;
         be->template launch<KR>(rgrid<KR>((i64)NROWBLK * lanes), r);
         df_final(a, &e);
         return be->ok() ? 0 : -1;
@@ -489,6 +509,7 @@ public:
         have_means = false;
         r.winmag = d_win;
         typedef KRow<RS, RPC, ROW_FWD_WINMAG> KR;
+        r.counter = d_counter;
         be->template launch<KR>(rgrid<KR>((i64)NROWBLK * lanes), r);
         return be->ok() ? 0 : -1;
     }
@@ -510,12 +531,13 @@ public:
         typedef KRowCorr<RS, RPC, 1> K1;
         i64 g = (i64)NROWBLK * lanes;
         if (g > (i64)be->num_sms * K1::MINB) g = (i64)be->num_sms * K1::MINB;
-        be->zero(d_counter, sizeof(int)); r.counter = d_counter;
+        r.counter = d_counter;
         be->template launch<K1>(dim3((unsigned)g, 1, 1), r);
         ColParams c{};
         c.src = d_B; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.invN = 1.0 / (double)N; c.nch = 1; c.nq = 1;
         c.part_key = d_keycol; c.part_stat = d_stat; c.ntx = NCOLTILE_I; c.ny = lanes;
         typedef KCol<CS, TSI, SRC_CF32, COL_INV_ARGMAX_STATS, 0, N2, 1> KCS;
+        c.pf_dist = pf_dist<KCS>();
         be->template launch<KCS>(pgrid<KCS>((i64)c.ntx * c.ny), c);
         PeakEvalParams pe{};
         pe.part_key = d_keycol; pe.npart = NCOLTILE_I; pe.B = d_B; pe.N = N; pe.nq = 1; pe.L1 = L1; pe.N2 = N2;
@@ -548,7 +570,7 @@ public:
             typedef KRowCorr<RS, RPC, 1> K1;
             const i64 wave = (i64)be->num_sms * K3::MINB;      // resident CTAs: TMEM columns are per CTA
             if (g > wave) g = wave;
-            be->zero(d_counter, sizeof(int)); r.counter = d_counter;
+            r.counter = d_counter;
             if (nq == 3) be->template launch<K3>(dim3((unsigned)g, 1, 1), r);
             else be->template launch<K1>(dim3((unsigned)g, 1, 1), r);
         };
@@ -557,6 +579,7 @@ public:
         c.src = d_B; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.invN = 1.0 / (double)N; c.nch = 1; c.nq = nq; c.part_key = d_keycol;
         c.ntx = NCOLTILE_I; c.ny = lanes * nq;
         typedef KCol<CS, TSI, SRC_CF32, COL_INV_ARGMAX, 0, N2, 1> KCI;
+        c.pf_dist = pf_dist<KCI>();
         be->template launch<KCI>(pgrid<KCI>((i64)c.ntx * c.ny), c);
         PeakEvalParams pe{};
         pe.part_key = d_keycol; pe.npart = nq * NCOLTILE_I; pe.B = d_B; pe.N = N; pe.nq = nq; pe.L1 = L1; pe.N2 = N2;
@@ -589,12 +612,13 @@ public:
         r.pdst = d_P; r.part_penergy = d_penergy;
         i64 g = (i64)NROWBLK * lanes;
         if (g > (i64)be->num_sms * K1::MINB) g = (i64)be->num_sms * K1::MINB;
-        be->zero(d_counter, sizeof(int)); r.counter = d_counter;
+        r.counter = d_counter;
         be->template launch<K1>(dim3((unsigned)g, 1, 1), r);
         ColParams c{};
         c.src = d_B; c.blob = d_blob_c; c.N = N; c.N2 = N2; c.invN = 1.0 / (double)N; c.nch = 1; c.nq = 1;
         c.part_key = d_keycol; c.ntx = NCOLTILE_I; c.ny = lanes;
         typedef KCol<CS, TSI, SRC_CF32, COL_INV_ARGMAX, 0, N2, 1> KCI;
+        c.pf_dist = pf_dist<KCI>();
         be->template launch<KCI>(pgrid<KCI>((i64)c.ntx * c.ny), c);
         FastPrepParams fp{};
         fp.key1 = d_keycol; fp.key2 = d_keycol2; fp.ntile = NCOLTILE_I; fp.tsi = TSI; fp.N2 = N2; fp.nrow = L1;
