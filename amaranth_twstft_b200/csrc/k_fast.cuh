@@ -181,24 +181,26 @@ struct KLagP {
             const float4* r2 = reinterpret_cast<const float4*>(p.R2 + lane * p.N2);
             const float4* u2 = reinterpret_cast<const float4*>(p.U2);
             const int npair = p.N2 / 2;
-            constexpr int U = 4;
-            int i = tid;
-            for (; i + (U - 1) * NT < npair; i += U * NT) {
+#ifndef TWSTFT_LAGP_U
+#define TWSTFT_LAGP_U 4
+#endif
+            constexpr int U = TWSTFT_LAGP_U;
+            // every pass requests U row pieces per thread before it uses the first; the last pass is predicated
+            // instead of falling back to one load at a time (pieces past the end contribute zero)
+            for (int i = tid; i < npair; i += U * NT) {
                 float4 a[U], b[U], c[U];
 #pragma unroll
-                for (int u = 0; u < U; u++) a[u] = row[i + u * NT];
+                for (int u = 0; u < U; u++) a[u] = (i + u * NT < npair) ? row[i + u * NT] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int u = 0; u < U; u++) { b[u] = r2[i + u * NT]; c[u] = u2[i + u * NT]; }
+                for (int u = 0; u < U; u++) {
+                    const int k = (i + u * NT < npair) ? i + u * NT : tid;
+                    b[u] = r2[k]; c[u] = u2[k];
+                }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     accumulate(make_float2(a[u].x, a[u].y), make_float2(b[u].x, b[u].y), make_float2(c[u].x, c[u].y), sr, ss);
                     accumulate(make_float2(a[u].z, a[u].w), make_float2(b[u].z, b[u].w), make_float2(c[u].z, c[u].w), sr, ss);
                 }
-            }
-            for (; i < npair; i += NT) {
-                const float4 a = row[i], b = r2[i], c = u2[i];
-                accumulate(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y), sr, ss);
-                accumulate(make_float2(a.z, a.w), make_float2(b.z, b.w), make_float2(c.z, c.w), sr, ss);
             }
             if ((p.N2 & 1) && tid == 0) {            // odd row length: the last sample alone
                 const int k2 = p.N2 - 1;
