@@ -21,7 +21,9 @@ typedef long long i64;
 
 struct Blk { int x, y, z, gx; };   // block index and gridDim.x
 
-enum SyncKind { SYNC_BARRIER = 0, SYNC_MAXKEY = 1, SYNC_SUMD = 2, SYNC_MAXKEY_SUMD = 3, SYNC_SUMF16 = 4 };
+enum SyncKind { SYNC_BARRIER = 0, SYNC_MAXKEY = 1, SYNC_SUMD = 2, SYNC_MAXKEY_SUMD = 3, SYNC_SUMF16 = 4,
+                SYNC_MAXKEY_ATOMIC = 5 };   // regs.key maximised over the CTA straight into *K::key_slot(p, blk, it) (zeroed
+                                            // by the host before the launch): warp shuffles + one atomic per warp, no barrier
 
 // ------------------------------------------------------------------ complex fp32 helpers
 // On sm_100a a complex value lives in an aligned 64-bit register pair and the arithmetic uses the

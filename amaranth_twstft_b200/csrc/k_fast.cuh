@@ -182,7 +182,7 @@ struct KLagP {
             const float4* u2 = reinterpret_cast<const float4*>(p.U2);
             const int npair = p.N2 / 2;
 #ifndef TWSTFT_LAGP_U
-#define TWSTFT_LAGP_U 4
+#define TWSTFT_LAGP_U 8
 #endif
             constexpr int U = TWSTFT_LAGP_U;
             // every pass requests U row pieces per thread before it uses the first; the last pass is predicated

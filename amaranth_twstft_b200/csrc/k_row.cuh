@@ -92,7 +92,15 @@ template <class S, int RPC, int MODE> struct KRow : DynChunk<(TWSTFT_ROW_DYNAMIC
     }
     static HD constexpr int sync_after(int ph)
     {
-        return (ph == NCOMP - 1 && MODE == ROW_FWD_ARGMAX) ? SYNC_MAXKEY : SYNC_BARRIER;
+        return (ph == NCOMP - 1 && MODE == ROW_FWD_ARGMAX) ? SYNC_MAXKEY_ATOMIC : SYNC_BARRIER;
+    }
+    // ROW_FWD_ARGMAX: the row's first-maximum key goes straight into its slot of part_key (zeroed by the host before
+    // the launch) with one atomic per warp that holds a candidate -- no block reduction, no barrier (it used to be two
+    // barriers and ~85 instructions per thread and row)
+    static HD u64* key_slot(const Params& p, const Blk& blk, int it)
+    {
+        const Work wk = work_of(p, blk, it);
+        return p.part_key + wk.lane * p.key_stride + p.key_off + wk.rowblk;
     }
     // work decomposition: item w -> (rowblk = w % nblk, lane = w / nblk)
     static HD int gx(const Params& p) { return p.nblk; }
@@ -292,11 +300,7 @@ template <class S, int RPC, int MODE> struct KRow : DynChunk<(TWSTFT_ROW_DYNAMIC
                 epilogue(p, wk, rl, j, r, gtab);
             }
         }
-        if (HASFIN && PH == NCOMP) {
-            if (tid == 0) {
-                if (MODE == ROW_FWD_ARGMAX) p.part_key[wk.lane * p.key_stride + p.key_off + wk.rowblk] = r.key;
-            }
-        }
+        // (phase NCOMP of ROW_FWD_ARGMAX is empty: the key was delivered by the SYNC_MAXKEY_ATOMIC step before it)
     }
 };
 

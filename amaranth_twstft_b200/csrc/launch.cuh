@@ -34,6 +34,18 @@ template <class K> __device__ __forceinline__ void block_max_key(typename K::Reg
     r.key = best;
 }
 
+// SYNC_MAXKEY_ATOMIC: no shared scratch, no barrier -- the result is only read by a later kernel
+template <class K> __device__ __forceinline__ void block_max_key_atomic(typename K::Regs& r, u64* slot)
+{
+    u64 k = r.key;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        u64 other = __shfl_xor_sync(0xffffffffu, k, o);
+        k = other > k ? other : k;
+    }
+    if ((threadIdx.x & 31) == 0 && k != 0) atomicMax(reinterpret_cast<unsigned long long*>(slot), (unsigned long long)k);
+}
+
 template <class K> __device__ __forceinline__ void block_sum_d(typename K::Regs& r, unsigned char* scratch)
 {
     static_assert(K::NSUM * 32 * 8 <= RED_SCRATCH_BYTES, "reduction scratch too small for this kernel's sums");
@@ -107,6 +119,7 @@ __device__ __forceinline__ void run_phases(const typename K::Params& p, const Bl
         if constexpr (kind == SYNC_MAXKEY || kind == SYNC_MAXKEY_SUMD) block_max_key<K>(r, scratch);
         if constexpr (kind == SYNC_SUMD || kind == SYNC_MAXKEY_SUMD) block_sum_d<K>(r, scratch);
         if constexpr (kind == SYNC_SUMF16) block_sum_f16<K>(r, scratch);
+        if constexpr (kind == SYNC_MAXKEY_ATOMIC) block_max_key_atomic<K>(r, K::key_slot(p, b, it));
         run_phases<K, PH + 1>(p, b, tid, r, smem, it, nit);
     }
 }

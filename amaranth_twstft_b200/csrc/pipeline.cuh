@@ -425,6 +425,7 @@ public:
             be->template launch<KDfFinal>(dim3(d.nsplit, max_lanes, 1), d);
         }
         typedef KRow<RS, RPC, MODE> KR;
+        if (MODE == ROW_FWD_ARGMAX) be->zero(d_keyrow, (size_t)max_lanes * NROWBLK * 2 * sizeof(u64));   // atomic maxima land here
         for (int par = 0; par < 2; par++) {
             if (e.power == 4) { if (par) col_raw<24>(a, 0, N * a.nch); else col_raw<14>(a, 0, N * a.nch); }
             else { if (par) col_raw<22>(a, 0, N * a.nch); else col_raw<12>(a, 0, N * a.nch); }
@@ -458,6 +459,7 @@ public:
         if (lanes > max_lanes) return -2;
         RowParams r = estimator_front(a, e);
         typedef KRow<RS, RPC, ROW_FWD_ARGMAX> KR;
+        be->zero(d_keyrow, (size_t)lanes * NROWBLK * 2 * sizeof(u64));       // the rows' atomic maxima land here
         r.counter = d_counter;
         be->template launch<KR>(rgrid<KR>((i64)NROWBLK * lanes), r);
         df_final(a, &e);

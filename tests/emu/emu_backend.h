@@ -31,6 +31,12 @@ template <class K, int PH> struct EmuPhases {
                     regs[0].dsum[i] = t;
                 }
             }
+            if constexpr (kind == SYNC_MAXKEY_ATOMIC) {
+                u64 best = 0;
+                for (int tid = 0; tid < K::NT; tid++) best = regs[tid].key > best ? regs[tid].key : best;
+                u64* slot = K::key_slot(p, b, it);
+                if (best > *slot) *slot = best;
+            }
             if constexpr (kind == SYNC_SUMF16) {
                 double t[16];
                 for (int i = 0; i < 16; i++) {
