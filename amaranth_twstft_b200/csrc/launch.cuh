@@ -29,8 +29,13 @@ template <class K> __device__ __forceinline__ void block_max_key(typename K::Reg
     if (lane == 0) s[warp] = k;
     __syncthreads();
     u64 best = s[0];
+    if constexpr (NW <= 8) {         // few warps: all partials requested at once (the rolled loop is a chain of NW
+#pragma unroll                       // shared-memory round trips at the very end of a short-lived CTA)
+        for (int w = 1; w < NW; w++) best = s[w] > best ? s[w] : best;
+    } else {
 #pragma unroll 1
-    for (int w = 1; w < NW; w++) best = s[w] > best ? s[w] : best;
+        for (int w = 1; w < NW; w++) best = s[w] > best ? s[w] : best;
+    }
     r.key = best;
 }
 
