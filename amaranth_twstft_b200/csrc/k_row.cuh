@@ -42,23 +42,12 @@ struct RowParams {
     int oa1, ob1, oa2, ob2;  // k2 ranges that can intersect the window (superset; exact test follows)
     unsigned k1mask;         // != 0: output-pruned form (KRow::PRUNABLE): bit k1 set <=> some k2 = k0 + R0 k1 + R0 R1 m of
                              // those ranges needs the middle-stage output k1; the last stage is then one dot product per bin
-    int* counter;            // dynamic work distribution of the estimator modes (launch.cuh)
     // ROW_FWD_WINMAG
     float* winmag;           // [lane][win_hi - win_lo + 1]  |X|^2 at shifted index s = win_lo + i
 };
 
-#ifndef TWSTFT_ROW_DYNAMIC
-#define TWSTFT_ROW_DYNAMIC 0
-#endif
-// estimator modes: work items dealt out CHUNK consecutive rows at a time through an atomic counter (launch.cuh)
-template <bool ON, int C> struct DynChunk {};
-template <int C> struct DynChunk<true, C> { static constexpr int CHUNK = C; };
-
-template <class S, int RPC, int MODE> struct KRow : DynChunk<(TWSTFT_ROW_DYNAMIC > 0) && MODE != ROW_FWD_STORE, TWSTFT_ROW_DYNAMIC> {
+template <class S, int RPC, int MODE> struct KRow {
     typedef RowParams Params;
-    static constexpr bool DYN = (TWSTFT_ROW_DYNAMIC > 0) && MODE != ROW_FWD_STORE;
-    static HD int total_items(const Params& p) { return (int)total_work(p); }
-    static HD int* counter(const Params& p) { return p.counter; }
     static const char* name()
     {
         return MODE == ROW_FWD_STORE ? "row_fwd_store" : MODE == ROW_FWD_ARGMAX ? "row_fwd_argmax" : "row_fwd_winmag";
@@ -113,7 +102,7 @@ template <class S, int RPC, int MODE> struct KRow : DynChunk<(TWSTFT_ROW_DYNAMIC
     struct Work { int rowblk, q; i64 lane; };
     static HD Work work_of(const Params& p, const Blk& blk, int it)
     {
-        const i64 w = DYN ? (i64)it : (i64)blk.x + (i64)it * blk.gx;
+        const i64 w = (i64)blk.x + (i64)it * blk.gx;
         const int g = gx(p);
         const int x = (int)(w % g);
         Work k;

@@ -118,7 +118,7 @@ public:
     template <class K> dim3 rgrid(i64 total) const
     {
         i64 g = (i64)be->num_sms * K::MINB * 8;
-        if (persistent || IsDynamic<K>::value) g = (i64)be->num_sms * K::MINB;
+        if (persistent) g = (i64)be->num_sms * K::MINB;
         if (g > total) g = total;
         if (g < 1) g = 1;
         return dim3((unsigned)g, 1, 1);
@@ -132,10 +132,9 @@ public:
         const int waves = col_pf >= 0 ? col_pf : (K::INVERSE ? 1 : 0);
         return persistent ? 0 : waves * be->num_sms * K::MINB;
     }
-    int col_items = 1;         // column passes: work items per CTA (1: one CTA per tile)
     template <class K> dim3 pgrid(i64 total) const
     {
-        i64 g = persistent ? (i64)be->num_sms * K::MINB : (total + col_items - 1) / col_items;
+        i64 g = persistent ? (i64)be->num_sms * K::MINB : total;
         if (g > total) g = total;
         if (g < 1) g = 1;
         return dim3((unsigned)g, 1, 1);
@@ -147,7 +146,6 @@ public:
         persistent = false;
         if (const char* e = getenv("TWSTFT_PERSISTENT")) persistent = atoi(e) != 0;
         if (const char* e = getenv("TWSTFT_COL_PF")) col_pf = atoi(e);
-        if (const char* e = getenv("TWSTFT_COL_ITEMS")) col_items = atoi(e) > 0 ? atoi(e) : 1;
         max_lanes = lanes;
         nq = nq_;
         std::vector<float2> blob(CS::BLOB + RS::BLOB + 4);
@@ -432,8 +430,7 @@ public:
             RowParams r = estimator_row(a, e, 2, par, 2 * N);
             r.key_off = par * NROWBLK;
             r.winmag = d_win;
-            r.counter = d_counter;
-        be->template launch<KR>(rgrid<KR>((i64)NROWBLK * lanes), r);
+            be->template launch<KR>(rgrid<KR>((i64)NROWBLK * lanes), r);
         }
         return 0;
     }
@@ -460,7 +457,6 @@ public:
         RowParams r = estimator_front(a, e);
         typedef KRow<RS, RPC, ROW_FWD_ARGMAX> KR;
         be->zero(d_keyrow, (size_t)lanes * NROWBLK * 2 * sizeof(u64));       // the rows' atomic maxima land here
-        r.counter = d_counter;
         be->template launch<KR>(rgrid<KR>((i64)NROWBLK * lanes), r);
         df_final(a, &e);
         return be->ok() ? 0 : -1;
@@ -511,7 +507,6 @@ public:
         have_means = false;
         r.winmag = d_win;
         typedef KRow<RS, RPC, ROW_FWD_WINMAG> KR;
-        r.counter = d_counter;
         be->template launch<KR>(rgrid<KR>((i64)NROWBLK * lanes), r);
         return be->ok() ? 0 : -1;
     }
