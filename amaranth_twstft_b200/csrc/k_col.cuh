@@ -70,7 +70,7 @@ template <class S, int TS, int SRC, int MODE, int OP = 0, int N2C = 0, int NCH =
         return MODE == COL_INV_ARGMAX ? "col_inv_argmax" : MODE == COL_INV_ARGMAX_STATS ? "col_inv_argmax_stats"
              : MODE == COL_INV_ARGMAX_K2 ? "col_inv_argmax_k2"
              : MODE == COL_INV_STORE ? "col_inv_store"
-             : SRC == SRC_RAW ? "col_fwd_raw" : SRC == SRC_BITS ? "col_fwd_bits" : OP != 0 ? "col_fwd_cf32_op" : "col_fwd_cf32";
+             : SRC == SRC_RAW ? ((OP % 10) >= 2 ? "col_fwd_raw_pow" : "col_fwd_raw") : SRC == SRC_BITS ? "col_fwd_bits" : OP != 0 ? "col_fwd_cf32_op" : "col_fwd_cf32";
     }
     static constexpr bool PERSISTENT = true;
     static constexpr bool INVERSE = (MODE != COL_FWD);

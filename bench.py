@@ -43,16 +43,16 @@ SURVEY_BYTES_PER_RECORD = 1.4e9  # 140*N bytes per channel
 # ALGORITHMIC bytes per lane (one channel of one record) and launch, in units of N bytes: SURVEY.md section 8d's
 # budget, item by item (mean 4N; x^p FFT 12N + 8N; derotate+FFT pass-1 12N; pass-2 32N + IFFT pass-1 32N = the work
 # of row_corr; IFFT pass-2 24N; the 16N of the SNR dot product have no kernel here: spectral identity).
-ALG_BYTES_N = {"mean": 4, "col_fwd_raw": 12, "row_fwd_argmax": 8, "row_corr": 64, "col_inv_argmax": 24}
+ALG_BYTES_N = {"mean": 4, "col_fwd_raw_pow": 12, "col_fwd_raw": 12, "row_fwd_argmax": 8, "row_corr": 64, "col_inv_argmax": 24}
 # bytes this design actually has to MOVE per lane and launch: row_corr keeps the product
 # spectrum and ffty on chip (tensor memory) and shares the code row through L2, 32N instead of 64N
-MOVED_BYTES_N = {"mean": 4, "col_fwd_raw": 12, "row_fwd_argmax": 8, "row_corr": 32, "col_inv_argmax": 24}
+MOVED_BYTES_N = {"mean": 4, "col_fwd_raw_pow": 12, "col_fwd_raw": 12, "row_fwd_argmax": 8, "row_corr": 32, "col_inv_argmax": 24}
 # fast peak path (k_fast.cuh, default): one inverse transform; row_corr reads A 8N, writes B 8N and P 8N; the column
 # pass reads 8N and does the job SURVEY budgets at 24N; the exact lags around the maximum read P once more (8N)
-ALG_BYTES_N_FAST = {"mean": 4, "col_fwd_raw": 12, "row_fwd_argmax": 8, "row_corr": 64, "col_inv_argmax": 24}
-MOVED_BYTES_N_FAST = {"mean": 4, "col_fwd_raw": 12, "row_fwd_argmax": 8, "row_corr": 24, "col_inv_argmax": 8,
+ALG_BYTES_N_FAST = {"mean": 4, "col_fwd_raw_pow": 12, "col_fwd_raw": 12, "row_fwd_argmax": 8, "row_corr": 64, "col_inv_argmax": 24}
+MOVED_BYTES_N_FAST = {"mean": 4, "col_fwd_raw_pow": 12, "col_fwd_raw": 12, "row_fwd_argmax": 8, "row_corr": 24, "col_inv_argmax": 8,
                       "fast_lag_p": 8}
-LAUNCHES_PER_LANE = {"col_fwd_raw": 2}          # estimator pass + derotated pass
+LAUNCHES_PER_LANE = {}     # every kernel of the table runs once per lane (col_fwd_raw_pow: x^2 estimator pass, col_fwd_raw: derotated pass)
 ALG_TOTAL_N = sum(v * LAUNCHES_PER_LANE.get(k, 1) for k, v in MOVED_BYTES_N.items())   # 92
 ALG_TOTAL_N_FAST = sum(v * LAUNCHES_PER_LANE.get(k, 1) for k, v in MOVED_BYTES_N_FAST.items())   # 76
 

@@ -26,7 +26,8 @@ NPTS = 5e6
 
 NAMES = [  # (regex on the demangled kernel name, bench.py kernel name)
     (r"KMean", "mean"),
-    (r"KCol<.*\b16, 0, 0, [12], 8000, 2>", "col_fwd_raw"),
+    (r"KCol<.*\b16, 0, 0, 2, 8000, 2>", "col_fwd_raw_pow"),
+    (r"KCol<.*\b16, 0, 0, 1, 8000, 2>", "col_fwd_raw"),
     (r"KRow<.*, 1, 1>", "row_fwd_argmax"),
     (r"KRowCorr<.*, 1, 1>", "row_corr"),
     (r"KCol<.*\b8, 1, 1, 0, 8000, 1>", "col_inv_argmax"),
