@@ -140,9 +140,9 @@ template <class K, class = void> struct HasPrologue { static constexpr bool valu
 template <class K> struct HasPrologue<K, decltype((void)&K::prologue)> { static constexpr bool value = true; };
 
 // Resident kernels with DYNAMIC work distribution declare K::CHUNK (items per grab), K::total_items(p) and
-// K::counter(p) (two device ints, zero before the first launch; the kernel leaves them at zero): a CTA takes the next CHUNK items with one atomicAdd
-// and `it` is then the GLOBAL item index.  SMs do not run at the same speed (L2 distance, co-resident CTAs), so a
-// static split of the items makes every launch as slow as its slowest SM.
+// K::counter(p) (two device ints, zero before the first launch; the kernel leaves them at zero): a CTA takes the
+// next CHUNK items with one atomicAdd and `it` is then the GLOBAL item index.  SMs do not run at the same speed (L2
+// distance, co-resident CTAs), so a static split of the items makes every launch as slow as its slowest SM.
 template <class K, class = void> struct IsDynamic { static constexpr bool value = false; };
 template <class K> struct IsDynamic<K, decltype((void)K::CHUNK)> { static constexpr bool value = true; };
 
