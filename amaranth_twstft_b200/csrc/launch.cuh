@@ -14,10 +14,21 @@ namespace twstft {
 constexpr int RED_SCRATCH_BYTES = 32 * 8 * 20;   // 32 warps x up to 20 doubles
 
 #ifdef __CUDACC__
+// Warp maximum of a 64-bit key with two REDUX instructions (value word, then the index word among the lanes that hold
+// the maximum value) instead of five shuffle rounds on register pairs; a key's low word is never 0 for a valid entry
+// (0xFFFFFFFF - index), an empty key is 0 in both words.
+__device__ __forceinline__ u64 warp_max_key(u64 k)
+{
+    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    return ((u64)mhi << 32) | (u64)mlo;
+}
+
 template <class K> __device__ __forceinline__ void block_max_key(typename K::Regs& r, unsigned char* scratch)
 {
-    u64 k = r.key;
-#pragma unroll
+    u64 k = r.key;                   // (shuffle rounds: the REDUX form of warp_max_key measured 5 % slower at the end of
+#pragma unroll                       //  the short-lived inverse-column CTAs, 1.6 % faster in the resident row pass)
     for (int o = 16; o > 0; o >>= 1) {
         u64 other = __shfl_xor_sync(0xffffffffu, k, o);
         k = other > k ? other : k;
@@ -42,12 +53,7 @@ template <class K> __device__ __forceinline__ void block_max_key(typename K::Reg
 // SYNC_MAXKEY_ATOMIC: no shared scratch, no barrier -- the result is only read by a later kernel
 template <class K> __device__ __forceinline__ void block_max_key_atomic(typename K::Regs& r, u64* slot)
 {
-    u64 k = r.key;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        u64 other = __shfl_xor_sync(0xffffffffu, k, o);
-        k = other > k ? other : k;
-    }
+    const u64 k = warp_max_key(r.key);
     if ((threadIdx.x & 31) == 0 && k != 0) atomicMax(reinterpret_cast<unsigned long long*>(slot), (unsigned long long)k);
 }
 
